@@ -1,0 +1,467 @@
+// dstep.cu -- the per-client discriminator step and generator-loss evaluation (K1/K2).
+// Reference: Worker.train, CGLGAN/2DMG/main.py:344-375; capgan.py:316-349; MDGAN/MNIST/mdgan.py:266-297.
+#include "gemm.cuh"
+
+namespace cgl {
+
+// ---------------------------------------------------------------------------------------------
+// Head kernel: last Linear (H -> nout, nout <= 2) + output activation + loss + its backward.
+// One CTA per group. Produces the loss, dZ of the last hidden layer, and (train) the Adam update
+// of the last layer.  BCE/CE/MSE follow torch.nn semantics (mean reduction per term; BCE log
+// clamped at -100; CE = log_softmax + nll).
+// ---------------------------------------------------------------------------------------------
+struct HeadParams {
+  int H, nout, rows, rows0;
+  const float* hin;  // [G][rows][H] last hidden activations
+  long long hin_gstride;
+  float* dz;  // [G][rows][H] out: grad wrt pre-activation of the last hidden layer
+  long long dz_gstride;
+  int hidden_act;
+  float slope;
+  float* params; float* adam_m; float* adam_v;  // packed rows (adam_* only when train)
+  long long ldp;
+  const int* ids;
+  long long w_off, b_off;
+  const int* step;
+  float lr, b1, b2, eps;
+  const int* n_valid0;  // [G] valid rows among the first rows0 (NULL: all)
+  int loss_kind, last_act;
+  float target0, target1;  // targets of rows [0,rows0) and [rows0,rows)
+  float scale;
+  float* out_loss;  // [G]
+  int train;
+};
+
+constexpr int HEAD_THREADS = 256;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const HeadParams p) {
+  extern __shared__ float smem[];
+  float* sW = smem;                        // [nout][H]
+  float* sdz = sW + p.nout * p.H;          // [rows][nout]
+  float* sloss = sdz + p.rows * p.nout;    // [rows]
+  float* sb = sloss + p.rows;              // [nout]
+
+  const int g = blockIdx.x;
+  const int rowid = p.ids ? p.ids[g] : g;
+  float* W = p.params + (long long)rowid * p.ldp + p.w_off;
+  float* Bv = p.params + (long long)rowid * p.ldp + p.b_off;
+  const float* hin = p.hin + (long long)g * p.hin_gstride;
+  float* dz = p.dz + (long long)g * p.dz_gstride;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nwarp = HEAD_THREADS / 32;
+  const int H = p.H, nout = p.nout;
+
+  for (int i = tid; i < nout * H; i += HEAD_THREADS) sW[i] = W[i];
+  if (tid < nout) sb[tid] = Bv[tid];
+  __syncthreads();
+
+  const int nv0 = p.n_valid0 ? min(p.n_valid0[g], p.rows0) : p.rows0;
+  const int n1 = p.rows - p.rows0;
+
+  // ---- logits, loss terms, d loss / d logits ----
+  for (int r = warp; r < p.rows; r += nwarp) {
+    const float* hr = hin + (long long)r * H;
+    float z0 = 0.f, z1 = 0.f;
+    for (int h = lane; h < H; h += 32) {
+      float a = hr[h];
+      z0 = fmaf(a, sW[h], z0);
+      if (nout == 2) z1 = fmaf(a, sW[H + h], z1);
+    }
+    z0 = warp_sum(z0);
+    if (nout == 2) z1 = warp_sum(z1);
+    if (lane == 0) {
+      const bool seg0 = r < p.rows0;
+      const bool valid = seg0 ? (r < nv0) : true;
+      const float t = seg0 ? p.target0 : p.target1;
+      const float wgt = valid ? p.scale / (float)(seg0 ? nv0 : n1) : 0.f;
+      z0 += sb[0];
+      if (nout == 2) z1 += sb[1];
+      float loss = 0.f, d0 = 0.f, d1 = 0.f;
+      if (p.loss_kind == CGL_LOSS_CE) {
+        // log_softmax + nll_loss, integer class target = (int)t
+        float mx = fmaxf(z0, z1);
+        float lse = mx + logf(expf(z0 - mx) + expf(z1 - mx));
+        int cls = (int)t;
+        loss = lse - (cls == 0 ? z0 : z1);
+        float s0 = expf(z0 - lse), s1 = expf(z1 - lse);
+        d0 = (s0 - (cls == 0 ? 1.f : 0.f)) * wgt;
+        d1 = (s1 - (cls == 1 ? 1.f : 0.f)) * wgt;
+      } else {
+        float o = act_fwd(z0, p.last_act, p.slope);
+        float dlo;  // d loss / d o
+        if (p.loss_kind == CGL_LOSS_BCE) {
+          float lo = fmaxf(logf(o), -100.f);
+          float l1o = fmaxf(logf(1.f - o), -100.f);
+          loss = -(t * lo + (1.f - t) * l1o);
+          dlo = (o - t) / fmaxf((1.f - o) * o, 1e-12f);
+        } else {  // MSE
+          float d = o - t;
+          loss = d * d;
+          dlo = 2.f * d;
+        }
+        d0 = dlo * wgt * act_bwd_from_out(o, p.last_act, p.slope);
+      }
+      if (!valid) { d0 = 0.f; d1 = 0.f; }  // padded rows of a ragged real batch carry no gradient
+      sloss[r] = valid ? loss : 0.f;
+      sdz[r * nout] = d0;
+      if (nout == 2) sdz[r * nout + 1] = d1;
+    }
+  }
+  __syncthreads();
+
+  if (tid == 0) {
+    float l0 = 0.f, l1 = 0.f;
+    for (int r = 0; r < p.rows0; ++r) l0 += sloss[r];
+    for (int r = p.rows0; r < p.rows; ++r) l1 += sloss[r];
+    float tot = 0.f;
+    if (nv0 > 0) tot += l0 / (float)nv0;
+    if (n1 > 0) tot += l1 / (float)n1;
+    p.out_loss[g] = tot * p.scale;
+  }
+
+  // ---- dZ of the last hidden layer: (dlogits . W) * act'(h) ----
+  for (int idx = tid; idx < p.rows * H; idx += HEAD_THREADS) {
+    int r = idx / H, h = idx - r * H;
+    float a = hin[idx];
+    float v = sdz[r * nout] * sW[h];
+    if (nout == 2) v = fmaf(sdz[r * nout + 1], sW[H + h], v);
+    dz[idx] = v * act_bwd_from_out(a, p.hidden_act, p.slope);
+  }
+
+  // ---- Adam on the last layer: dW[j][h] = sum_r dlogit[r][j] * h[r][h]; db[j] = sum_r dlogit[r][j]
+  if (p.train) {
+    const AdamScalars s = make_adam_scalars(p.step[rowid], p.lr, p.b1, p.b2, p.eps);
+    float* Mo = p.adam_m + (long long)rowid * p.ldp;
+    float* Vo = p.adam_v + (long long)rowid * p.ldp;
+    for (int h = tid; h < H; h += HEAD_THREADS) {
+      float g0 = 0.f, g1 = 0.f;
+      for (int r = 0; r < p.rows; ++r) {
+        float a = hin[(long long)r * H + h];
+        g0 = fmaf(sdz[r * nout], a, g0);
+        if (nout == 2) g1 = fmaf(sdz[r * nout + 1], a, g1);
+      }
+      {
+        long long o = p.w_off + h;
+        float w = sW[h], mm = Mo[o], vv = Vo[o];
+        adam_update(w, mm, vv, g0, s);
+        W[h] = w; Mo[o] = mm; Vo[o] = vv;
+      }
+      if (nout == 2) {
+        long long o = p.w_off + H + h;
+        float w = sW[H + h], mm = Mo[o], vv = Vo[o];
+        adam_update(w, mm, vv, g1, s);
+        W[H + h] = w; Mo[o] = mm; Vo[o] = vv;
+      }
+    }
+    if (tid < nout) {
+      float gb = 0.f;
+      for (int r = 0; r < p.rows; ++r) gb += sdz[r * nout + tid];
+      long long o = p.b_off + tid;
+      float w = sb[tid], mm = Mo[o], vv = Vo[o];
+      adam_update(w, mm, vv, gb, s);
+      Bv[tid] = w; Mo[o] = mm; Vo[o] = vv;
+    }
+  }
+}
+
+__global__ void bump_step_kernel(int G, int* step, const int* ids) {
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < G) step[ids ? ids[g] : g] += 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+static int validate_d_arch(const cgl_mlp_desc* a, int loss_kind) {
+  CGL_REQUIRE(a != nullptr, "arch is NULL");
+  CGL_REQUIRE(a->n_layers >= 2 && a->n_layers <= CGL_MAX_LAYERS, "discriminator needs 2..%d Linear layers, got %d",
+              CGL_MAX_LAYERS, a->n_layers);
+  for (int i = 0; i < a->n_layers; ++i) {
+    CGL_REQUIRE(a->dims[i] > 0 && a->dims[i + 1] > 0, "bad layer width at layer %d", i);
+    CGL_REQUIRE(a->bn[i] == 0, "BatchNorm is not supported inside a discriminator (layer %d)", i);
+  }
+  const int nout = a->dims[a->n_layers];
+  const int last = a->act[a->n_layers - 1];
+  switch (loss_kind) {
+    case CGL_LOSS_BCE:
+      CGL_REQUIRE(nout == 1 && last == CGL_ACT_SIGMOID, "BCE needs a 1-logit sigmoid discriminator (reference pairing, SURVEY 3.5.5)");
+      break;
+    case CGL_LOSS_CE:
+      CGL_REQUIRE(nout == 2 && last == CGL_ACT_NONE, "CrossEntropy needs a 2-logit discriminator without output activation");
+      break;
+    case CGL_LOSS_MSE:
+      CGL_REQUIRE(nout == 1 && (last == CGL_ACT_NONE || last == CGL_ACT_SIGMOID), "MSE needs a 1-output discriminator");
+      break;
+    default:
+      set_error("unknown loss kind %d", loss_kind);
+      return CGL_EINVAL;
+  }
+  CGL_REQUIRE(a->dims[a->n_layers - 1] <= 4096, "last hidden width too large for the head kernel");
+  return CGL_OK;
+}
+
+static size_t acts_floats(const cgl_mlp_desc* a, int G, int rows) {
+  size_t n = 0;
+  for (int i = 1; i < a->n_layers; ++i) n += (size_t)G * rows * a->dims[i];
+  return n;
+}
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct Workspace {
+  float* H[CGL_MAX_LAYERS];   // H[i], i=1..L-1 : [G][rows][dims[i]]
+  float* dZ[CGL_MAX_LAYERS];  // same shapes
+};
+static Workspace carve(const cgl_mlp_desc* a, int G, int rows, void* ws) {
+  Workspace w;
+  char* p = (char*)ws;
+  for (int i = 1; i < a->n_layers; ++i) {
+    size_t bytes = align_up((size_t)G * rows * a->dims[i] * sizeof(float), 256);
+    w.H[i] = (float*)p; p += bytes;
+    w.dZ[i] = (float*)p; p += bytes;
+  }
+  return w;
+}
+static size_t ws_bytes(const cgl_mlp_desc* a, int G, int rows) {
+  size_t b = 0;
+  for (int i = 1; i < a->n_layers; ++i) b += 2 * align_up((size_t)G * rows * a->dims[i] * sizeof(float), 256);
+  return b + 256;
+}
+
+// ---- GemmParams builders ------------------------------------------------------------------
+// y[g][r][o] = act( sum_i x[g][r][i] * W[g][o][i] + b[g][o] )
+static GemmParams fwd_params(int rows, int in, int out, const RowMap& X, const float* params, long long ldp,
+                             const int* ids, long long w_off, long long b_off, int act, float slope, float* y,
+                             long long y_gstride) {
+  GemmParams p = {};
+  p.M = rows; p.N = out; p.K = in;
+  p.A = X;
+  p.B = single_rows(params + w_off, ldp, ids, in);
+  p.cbase = y; p.c_gstride = y_gstride; p.cidx = nullptr; p.c_off = 0; p.ldc = out;
+  p.c_vec = (aligned16(y) && out % 4 == 0 && y_gstride % 4 == 0) ? 1 : 0;
+  p.bias_base = (b_off >= 0) ? params : nullptr; p.bias_gstride = ldp; p.bias_idx = ids; p.bias_off = b_off;
+  p.act = act; p.slope = slope;
+  p.dbias_off = -1;
+  return p;
+}
+// dx[g][r][i] = ( sum_o dy[g][r][o] * W[g][o][i] ) * act'(saved[g][r][i])
+static GemmParams bwd_data_params(int rows, int in, int out, const float* dy, long long dy_gstride,
+                                  const float* params, long long ldp, const int* ids, long long w_off,
+                                  const float* saved, long long saved_gstride, int act, float slope, float* dx,
+                                  long long dx_gstride) {
+  GemmParams p = {};
+  p.M = rows; p.N = in; p.K = out;
+  p.A = single_rows(dy, dy_gstride, nullptr, out);
+  p.B = single_rows(params + w_off, ldp, ids, in);  // row = contraction index o, contiguous along i
+  p.cbase = dx; p.c_gstride = dx_gstride; p.cidx = nullptr; p.c_off = 0; p.ldc = in;
+  p.c_vec = (aligned16(dx) && in % 4 == 0 && dx_gstride % 4 == 0) ? 1 : 0;
+  p.saved = saved; p.saved_gstride = saved_gstride;
+  p.act = act; p.slope = slope;
+  p.dbias_off = -1;
+  return p;
+}
+// dW[g][o][i] = sum_r dy[g][r][o] * x[g][r][i]   (+ db[g][o] = sum_r dy[g][r][o])
+static GemmParams wgrad_params(int rows, int in, int out, const float* dy, long long dy_gstride, const RowMap& X,
+                               float* base, long long ld, const int* ids, long long w_off, long long b_off) {
+  GemmParams p = {};
+  p.M = out; p.N = in; p.K = rows;
+  p.A = single_rows(dy, dy_gstride, nullptr, out);  // row = contraction index r, contiguous along o
+  p.B = X;                                           // row = contraction index r, contiguous along i
+  p.cbase = base; p.c_gstride = ld; p.cidx = ids; p.c_off = w_off; p.ldc = in;
+  p.c_vec = (aligned16(base) && ld % 4 == 0 && w_off % 4 == 0 && in % 4 == 0) ? 1 : 0;
+  p.bias_off = b_off; p.dbias_off = b_off;
+  return p;
+}
+
+static int forward_hidden(const cgl_mlp_desc* a, const cgl_mlp_layout& lay, int G, int rows, const RowMap& X,
+                          const float* params, long long ldp, const int* ids, Workspace& w, cudaStream_t st) {
+  for (int l = 0; l + 1 < a->n_layers; ++l) {
+    RowMap A = (l == 0) ? X : single_rows(w.H[l], (long long)rows * a->dims[l], nullptr, a->dims[l]);
+    GemmParams p = fwd_params(rows, a->dims[l], a->dims[l + 1], A, params, ldp, ids, lay.w_off[l], lay.b_off[l],
+                              a->act[l], a->lrelu_slope, w.H[l + 1], (long long)rows * a->dims[l + 1]);
+    CGL_CHECK_CUDA((launch_grouped_gemm<true, true, EPI_FWD>(p, G, st)));
+  }
+  return CGL_OK;
+}
+
+static int launch_head(const cgl_mlp_desc* a, const cgl_mlp_layout& lay, int G, int rows, int rows0, Workspace& w,
+                       float* params, float* am, float* av, long long ldp, const int* ids, const int* step,
+                       const cgl_train_cfg* cfg, int loss_kind, float scale, const int* n_valid0, float t0, float t1,
+                       float* out_loss, int train, cudaStream_t st) {
+  const int L = a->n_layers;
+  HeadParams h = {};
+  h.H = a->dims[L - 1]; h.nout = a->dims[L]; h.rows = rows; h.rows0 = rows0;
+  h.hin = w.H[L - 1]; h.hin_gstride = (long long)rows * h.H;
+  h.dz = w.dZ[L - 1]; h.dz_gstride = (long long)rows * h.H;
+  h.hidden_act = a->act[L - 2]; h.slope = a->lrelu_slope;
+  h.params = params; h.adam_m = am; h.adam_v = av; h.ldp = ldp; h.ids = ids;
+  h.w_off = lay.w_off[L - 1]; h.b_off = lay.b_off[L - 1];
+  h.step = step;
+  if (cfg) { h.lr = cfg->lr; h.b1 = cfg->beta1; h.b2 = cfg->beta2; h.eps = cfg->eps; }
+  h.n_valid0 = n_valid0;
+  h.loss_kind = loss_kind; h.last_act = a->act[L - 1];
+  h.target0 = t0; h.target1 = t1; h.scale = scale;
+  h.out_loss = out_loss; h.train = train;
+  size_t smem = (size_t)(h.nout * h.H + rows * h.nout + rows + h.nout) * sizeof(float);
+  if (smem > 48 * 1024) {
+    CGL_CHECK_CUDA(cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+  head_kernel<<<G, HEAD_THREADS, smem, st>>>(h);
+  CGL_CHECK_LAUNCH();
+  return CGL_OK;
+}
+
+}  // namespace cgl
+
+using namespace cgl;
+
+extern "C" size_t cgl_d_step_workspace_bytes(const cgl_mlp_desc* arch, int G, int B) {
+  if (!arch || G <= 0 || B <= 0) return 0;
+  return ws_bytes(arch, G, 2 * B);
+}
+extern "C" size_t cgl_g_loss_workspace_bytes(const cgl_mlp_desc* arch, int G, int B) {
+  if (!arch || G <= 0 || B <= 0) return 0;
+  return ws_bytes(arch, G, B);
+}
+
+extern "C" int cgl_d_step(const cgl_mlp_desc* arch, int G, float* params, float* adam_m, float* adam_v, int64_t ldp,
+                          int32_t* step, const int32_t* client_ids, const float* real, const int32_t* n_real,
+                          const float* fake, const int32_t* fake_idx, int B, const cgl_train_cfg* cfg,
+                          float* out_dloss, void* workspace, size_t workspace_bytes, cgl_stream_t stream) {
+  CGL_REQUIRE(cfg != nullptr, "cfg is NULL");
+  int rc = validate_d_arch(arch, cfg->loss_kind);
+  if (rc) return rc;
+  if (G == 0) return CGL_OK;
+  CGL_REQUIRE(G > 0 && G <= 65535, "G=%d out of range (1..65535 groups per call)", G);
+  CGL_REQUIRE(B > 0, "B must be positive");
+  CGL_REQUIRE(params && adam_m && adam_v && step && real && fake && out_dloss && workspace, "NULL tensor pointer");
+  cgl_mlp_layout lay;
+  rc = cgl_mlp_layout_of(arch, &lay);
+  if (rc) return rc;
+  CGL_REQUIRE(ldp >= lay.n_params, "ldp=%lld smaller than packed row (%lld)", (long long)ldp, (long long)lay.n_params);
+  const int rows = 2 * B;
+  if (workspace_bytes < ws_bytes(arch, G, rows)) {
+    set_error("workspace too small: %zu < %zu", workspace_bytes, ws_bytes(arch, G, rows));
+    return CGL_EWORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  Workspace w = carve(arch, G, rows, workspace);
+  const int L = arch->n_layers;
+  const int d = arch->dims[0];
+
+  bump_step_kernel<<<(G + 127) / 128, 128, 0, st>>>(G, step, client_ids);
+  CGL_CHECK_LAUNCH();
+
+  // rows [0,B): real[g], rows [B,2B): fake[fake_idx[g]]   (CGLGAN/2DMG/main.py:361-363)
+  RowMap X = dual_rows(real, (long long)B * d, nullptr, B, fake, (long long)B * d, fake_idx, d);
+  rc = forward_hidden(arch, lay, G, rows, X, params, ldp, client_ids, w, st);
+  if (rc) return rc;
+  // loss(D(real), 1) + loss(D(fake), 0); Adam on the last layer
+  rc = launch_head(arch, lay, G, rows, B, w, params, adam_m, adam_v, ldp, client_ids, step, cfg, cfg->loss_kind,
+                   cfg->d_loss_scale, n_real, 1.f, 0.f, out_dloss, 1, st);
+  if (rc) return rc;
+  for (int l = L - 2; l >= 0; --l) {
+    const int in = arch->dims[l], out = arch->dims[l + 1];
+    if (l > 0) {
+      GemmParams p = bwd_data_params(rows, in, out, w.dZ[l + 1], (long long)rows * out, params, ldp, client_ids,
+                                     lay.w_off[l], w.H[l], (long long)rows * in, arch->act[l - 1], arch->lrelu_slope,
+                                     w.dZ[l], (long long)rows * in);
+      CGL_CHECK_CUDA((launch_grouped_gemm<true, false, EPI_BWD_DATA>(p, G, st)));
+    }
+    RowMap Xin = (l == 0) ? X : single_rows(w.H[l], (long long)rows * in, nullptr, in);
+    GemmParams p = wgrad_params(rows, in, out, w.dZ[l + 1], (long long)rows * out, Xin, params, ldp, client_ids,
+                                lay.w_off[l], lay.b_off[l]);
+    p.adam_m = adam_m; p.adam_v = adam_v; p.step = step;
+    p.lr = cfg->lr; p.b1 = cfg->beta1; p.b2 = cfg->beta2; p.eps = cfg->eps;
+    CGL_CHECK_CUDA((launch_grouped_gemm<false, false, EPI_ADAM>(p, G, st)));
+  }
+  return CGL_OK;
+}
+
+extern "C" int cgl_g_loss(const cgl_mlp_desc* arch, int G, const float* params, int64_t ldp,
+                          const int32_t* client_ids, const float* xg, const int32_t* xg_idx, int B, int loss_kind,
+                          float* out_loss, float* out_dxg, void* workspace, size_t workspace_bytes,
+                          cgl_stream_t stream) {
+  int rc = validate_d_arch(arch, loss_kind);
+  if (rc) return rc;
+  if (G == 0) return CGL_OK;
+  CGL_REQUIRE(G > 0 && G <= 65535, "G=%d out of range (1..65535 groups per call)", G);
+  CGL_REQUIRE(B > 0, "B must be positive");
+  CGL_REQUIRE(params && xg && out_loss && workspace, "NULL tensor pointer");
+  cgl_mlp_layout lay;
+  rc = cgl_mlp_layout_of(arch, &lay);
+  if (rc) return rc;
+  CGL_REQUIRE(ldp >= lay.n_params, "ldp smaller than packed row");
+  if (workspace_bytes < ws_bytes(arch, G, B)) {
+    set_error("workspace too small: %zu < %zu", workspace_bytes, ws_bytes(arch, G, B));
+    return CGL_EWORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  Workspace w = carve(arch, G, B, workspace);
+  const int L = arch->n_layers;
+  const int d = arch->dims[0];
+  RowMap X = single_rows(xg, (long long)B * d, xg_idx, d);
+  rc = forward_hidden(arch, lay, G, B, X, params, ldp, client_ids, w, st);
+  if (rc) return rc;
+  // G_loss = loss(D(Xg), valid)   (CGLGAN/2DMG/main.py:368-372); no parameter update
+  rc = launch_head(arch, lay, G, B, B, w, const_cast<float*>(params), nullptr, nullptr, ldp, client_ids, nullptr,
+                   nullptr, loss_kind, 1.f, nullptr, 1.f, 1.f, out_loss, 0, st);
+  if (rc) return rc;
+  if (!out_dxg) return CGL_OK;
+  for (int l = L - 2; l >= 0; --l) {
+    const int in = arch->dims[l], out = arch->dims[l + 1];
+    if (l > 0) {
+      GemmParams p = bwd_data_params(B, in, out, w.dZ[l + 1], (long long)B * out, params, ldp, client_ids,
+                                     lay.w_off[l], w.H[l], (long long)B * in, arch->act[l - 1], arch->lrelu_slope,
+                                     w.dZ[l], (long long)B * in);
+      CGL_CHECK_CUDA((launch_grouped_gemm<true, false, EPI_BWD_DATA>(p, G, st)));
+    } else {
+      GemmParams p = bwd_data_params(B, in, out, w.dZ[1], (long long)B * out, params, ldp, client_ids, lay.w_off[0],
+                                     nullptr, 0, CGL_ACT_NONE, 0.f, out_dxg, (long long)B * in);
+      CGL_CHECK_CUDA((launch_grouped_gemm<true, false, EPI_STORE>(p, G, st)));
+    }
+  }
+  return CGL_OK;
+}
+
+// ---- building blocks ------------------------------------------------------------------------
+extern "C" int cgl_linear_fwd(int G, int rows, int in, int out, const float* x, int64_t x_gstride, const float* wbase,
+                              int64_t ldp, const int32_t* ids, int64_t w_off, int64_t b_off, int act, float slope,
+                              float* y, int64_t y_gstride, cgl_stream_t stream) {
+  CGL_REQUIRE(G >= 0 && G <= 65535 && rows > 0 && in > 0 && out > 0, "bad shape");
+  CGL_REQUIRE(x && wbase && y, "NULL tensor pointer");
+  RowMap X = single_rows(x, x_gstride, nullptr, in);
+  GemmParams p = fwd_params(rows, in, out, X, wbase, ldp, ids, w_off, b_off, act, slope, y, y_gstride);
+  CGL_CHECK_CUDA((launch_grouped_gemm<true, true, EPI_FWD>(p, G, (cudaStream_t)stream)));
+  return CGL_OK;
+}
+
+extern "C" int cgl_linear_bwd_data(int G, int rows, int in, int out, const float* dy, int64_t dy_gstride,
+                                   const float* wbase, int64_t ldp, const int32_t* ids, int64_t w_off,
+                                   const float* saved, int64_t saved_gstride, int act, float slope, float* dx,
+                                   int64_t dx_gstride, cgl_stream_t stream) {
+  CGL_REQUIRE(G >= 0 && G <= 65535 && rows > 0 && in > 0 && out > 0, "bad shape");
+  CGL_REQUIRE(dy && wbase && dx, "NULL tensor pointer");
+  GemmParams p = bwd_data_params(rows, in, out, dy, dy_gstride, wbase, ldp, ids, w_off, saved, saved_gstride, act,
+                                 slope, dx, dx_gstride);
+  if (saved) {
+    CGL_CHECK_CUDA((launch_grouped_gemm<true, false, EPI_BWD_DATA>(p, G, (cudaStream_t)stream)));
+  } else {
+    CGL_CHECK_CUDA((launch_grouped_gemm<true, false, EPI_STORE>(p, G, (cudaStream_t)stream)));
+  }
+  return CGL_OK;
+}
+
+extern "C" int cgl_linear_wgrad(int G, int rows, int in, int out, const float* dy, int64_t dy_gstride, const float* x,
+                                int64_t x_gstride, float* gbase, int64_t ldg, const int32_t* ids, int64_t w_off,
+                                int64_t b_off, cgl_stream_t stream) {
+  CGL_REQUIRE(G >= 0 && G <= 65535 && rows > 0 && in > 0 && out > 0, "bad shape");
+  CGL_REQUIRE(dy && x && gbase, "NULL tensor pointer");
+  RowMap X = single_rows(x, x_gstride, nullptr, in);
+  GemmParams p = wgrad_params(rows, in, out, dy, dy_gstride, X, gbase, ldg, ids, w_off, b_off);
+  CGL_CHECK_CUDA((launch_grouped_gemm<false, false, EPI_STORE>(p, G, (cudaStream_t)stream)));
+  return CGL_OK;
+}

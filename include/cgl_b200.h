@@ -1,0 +1,197 @@
+/*
+ * cgl_b200.h -- C ABI of the B200 (sm_100a) engine for the CGL-GAN simulated-client hot path.
+ *
+ * The reference (NetworkCommunication/CGL-GAN) is pure Python/PyTorch and has no FFI of its own;
+ * its "operator interface" for this path is the body of Worker.train / Server.train / Cloud.run.
+ * Each entry point below names the reference code it replaces (file:line under /root/reference).
+ *
+ * Conventions
+ *   - every function returns 0 on success and a negative CGL_E* code on failure; it never throws
+ *     and never allocates device memory. cgl_last_error() gives a human-readable reason.
+ *   - all tensor pointers are CALLER-OWNED DEVICE pointers (fp32 unless stated, indices int32).
+ *   - every compute call is asynchronous on the cudaStream_t passed as `stream` (cgl_stream_t).
+ *   - "packed row": one client's parameters as a flat fp32 vector in torch `parameters()` order
+ *     (= fedlab SerializationTool.serialize_model order, capgan.py:170), rows `ldp` floats apart.
+ */
+#ifndef CGL_B200_H
+#define CGL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* cgl_stream_t; /* a cudaStream_t */
+typedef void* cgl_comm_t;   /* opaque communicator (wraps an ncclComm_t) */
+
+/* ---- error codes ---- */
+#define CGL_OK 0
+#define CGL_EINVAL (-1)     /* bad argument (NULL pointer, unsupported arch/loss pairing, ...) */
+#define CGL_EWORKSPACE (-2) /* workspace too small */
+#define CGL_ECUDA (-3)      /* a CUDA runtime call / kernel launch failed */
+#define CGL_ENCCL (-4)      /* NCCL unavailable or an NCCL call failed */
+#define CGL_EUNSUPPORTED (-5)
+
+/* ---- activations / losses ---- */
+#define CGL_ACT_NONE 0
+#define CGL_ACT_LRELU 1 /* LeakyReLU(0.2): CGLGAN/2DMG/model.py:60 */
+#define CGL_ACT_TANH 2
+#define CGL_ACT_SIGMOID 3
+
+#define CGL_LOSS_BCE 0 /* nn.BCELoss on a sigmoid output: CGLGAN/2DMG/main.py:336,361-364 */
+#define CGL_LOSS_CE 1  /* nn.CrossEntropyLoss on 2 logits: capgan.py:324-339 */
+#define CGL_LOSS_MSE 2 /* LSGAN least-squares (no call site in the reference; parity unpinned) */
+
+/* ---- architectures known to cgl_arch_describe ---- */
+#define CGL_ARCH_D_2D 0      /* 2->128->256->1 sigmoid : CGLGAN/2DMG/model.py:54-71 */
+#define CGL_ARCH_D_MNIST1 1  /* 784->512->256->1 sigmoid: CGLGAN/MNIST/mnist_model.py:69-86 */
+#define CGL_ARCH_D_MNIST2 2  /* 784->512->256->2 logits : model/mnist_model.py:71-88 */
+#define CGL_ARCH_D_MNIST_LS 3 /* 784->512->256->1 linear (LSGAN/MSE variant of D_MNIST1) */
+#define CGL_ARCH_G_2D_MD 4   /* 100->256->128->2 tanh   : MDGAN/2DMG/model.py:4-21 */
+#define CGL_ARCH_G_MNIST 5   /* 100->128->256bn->512bn->1024bn->784 tanh: model/mnist_model.py:5-29 */
+#define CGL_ARCH_G_2D_TRUNK 6  /* 100->32 lrelu           : CGLGAN/2DMG/model.py:30-33 */
+#define CGL_ARCH_G_2D_HEAD 7   /* 32->2 tanh              : CGLGAN/2DMG/model.py:36-41 */
+#define CGL_ARCH_G_MNIST_TRUNK 8 /* 100->128->256bn->512bn : model/mnist_model.py:45-49 */
+#define CGL_ARCH_G_MNIST_HEAD 9  /* 512->1024bn->784 tanh  : model/mnist_model.py:52-57 */
+#define CGL_NUM_ARCH 10
+
+#define CGL_MAX_LAYERS 8
+
+/* A stack of Linear[+BatchNorm1d]+activation layers. */
+typedef struct cgl_mlp_desc {
+  int32_t n_layers;                 /* number of Linear layers */
+  int32_t dims[CGL_MAX_LAYERS + 1]; /* dims[0] = input width, dims[i+1] = out features of layer i */
+  int32_t act[CGL_MAX_LAYERS];      /* CGL_ACT_* applied after layer i (after BN if bn[i]) */
+  int32_t bn[CGL_MAX_LAYERS];       /* 1: BatchNorm1d(out, eps=bn_eps) between Linear i and act */
+  float bn_eps;                     /* 0.8 in the reference (2nd positional arg of BatchNorm1d) */
+  float bn_momentum;                /* 0.1 */
+  float lrelu_slope;                /* 0.2 */
+} cgl_mlp_desc;
+
+/* Offsets (in floats) of each parameters() entry inside a packed row. */
+typedef struct cgl_mlp_layout {
+  int64_t n_params;                   /* P: total floats in a packed row */
+  int64_t w_off[CGL_MAX_LAYERS];      /* Linear.weight [out,in] row-major */
+  int64_t b_off[CGL_MAX_LAYERS];      /* Linear.bias   [out] */
+  int64_t bn_w_off[CGL_MAX_LAYERS];   /* BatchNorm.weight [out], -1 if none */
+  int64_t bn_b_off[CGL_MAX_LAYERS];   /* BatchNorm.bias   [out], -1 if none */
+  int64_t n_bn_stats;                 /* floats of running_mean+running_var (kept in a second row) */
+  int64_t bn_mean_off[CGL_MAX_LAYERS]; /* offset inside the stats row, -1 if none */
+  int64_t bn_var_off[CGL_MAX_LAYERS];
+} cgl_mlp_layout;
+
+/* Optimiser / loss knobs of one discriminator step. */
+typedef struct cgl_train_cfg {
+  int32_t loss_kind;  /* CGL_LOSS_* */
+  float d_loss_scale; /* 0.5 in capgan.py:339 / mixed-gan.py:382, 1.0 elsewhere */
+  float lr;           /* lr_d = 2e-4: CGLGAN/2DMG/main.py:284 */
+  float beta1, beta2; /* b1=0.5, b2=0.999: CGLGAN/2DMG/main.py:55-56 */
+  float eps;          /* torch.optim.Adam default 1e-8 */
+} cgl_train_cfg;
+
+/* ---- introspection ---- */
+const char* cgl_version(void);
+const char* cgl_last_error(void);
+/* 1 if a CUDA device with compute capability 10.x is usable, 0 otherwise (never fails). */
+int cgl_device_ok(void);
+
+/* Replaces: the model constructors (a6) as far as shapes go. */
+int cgl_arch_describe(int arch_id, cgl_mlp_desc* out_desc);
+/* Replaces: SerializationTool.serialize_model ordering (capgan.py:170, fegan.py:133-134). */
+int cgl_mlp_layout_of(const cgl_mlp_desc* desc, cgl_mlp_layout* out_layout);
+
+/* ---- K1/K2: the per-client discriminator step -------------------------------------------
+ * Replaces Worker.train's D loop: CGLGAN/2DMG/main.py:349-366 (BCE), capgan.py:324-341 (CE x0.5),
+ * MDGAN/MNIST/mdgan.py:270-288, ACGAN/MNIST/acgan.py:273-292, and the Adam step (a7).
+ * For each of the G groups (clients) g:
+ *     row   = client_ids ? client_ids[g] : g                 (row of params/adam_m/adam_v/step)
+ *     L     = loss(D(real[g][0:n_real[g]]), valid) + loss(D(fake[fake_idx ? fake_idx[g] : g]), fake)
+ *     out_dloss[g] = d_loss_scale * L ; backward ; step[row] += 1 ; Adam(row)
+ * real is [G, B, d] (rows >= n_real[g] are ignored), fake is [*, B, d]; n_real NULL means all B.
+ * workspace must hold cgl_d_step_workspace_bytes(arch, G, B) bytes.                       */
+size_t cgl_d_step_workspace_bytes(const cgl_mlp_desc* arch, int G, int B);
+int cgl_d_step(const cgl_mlp_desc* arch, int G, float* params, float* adam_m, float* adam_v,
+               int64_t ldp, int32_t* step, const int32_t* client_ids, const float* real,
+               const int32_t* n_real, const float* fake, const int32_t* fake_idx, int B,
+               const cgl_train_cfg* cfg, float* out_dloss, void* workspace, size_t workspace_bytes,
+               cgl_stream_t stream);
+
+/* ---- K1/K2: generator-loss evaluation through each client's (updated) D -------------------
+ * Replaces Worker.train's tail: CGLGAN/2DMG/main.py:368-373, capgan.py:343-347 -- and the part of
+ * Server.train's backward that runs through every client's D (CGLGAN/2DMG/main.py:257,268):
+ *     out_loss[g] = loss(D_row(xg[xg_idx ? xg_idx[g] : g]), valid)
+ *     out_dxg[g]  = d out_loss[g] / d xg        ([G, B, d]; may be NULL)
+ * This is the (client_idx, F_grad, F_pred) hand-off sketched at CGLGAN/MNIST/main.py:220-235.  */
+size_t cgl_g_loss_workspace_bytes(const cgl_mlp_desc* arch, int G, int B);
+int cgl_g_loss(const cgl_mlp_desc* arch, int G, const float* params, int64_t ldp,
+               const int32_t* client_ids, const float* xg, const int32_t* xg_idx, int B,
+               int loss_kind, float* out_loss, float* out_dxg, void* workspace,
+               size_t workspace_bytes, cgl_stream_t stream);
+
+/* out[s] = sum_{j in [srv_ptr[s], srv_ptr[s+1])} weights[clients[j]] * dxg[clients[j]]
+ * (weights NULL = 1, clients NULL = identity). Replaces the accumulation of every client's
+ * dLoss/dXg into a shared Xg during F_max.backward(): capgan.py:258, MDGAN/MNIST/mdgan.py:203-204. */
+int cgl_dxg_reduce(int S, const int32_t* srv_ptr, const int32_t* clients, const float* weights,
+                   const float* dxg, int64_t n /* B*d floats per client */, float* out,
+                   cgl_stream_t stream);
+
+/* ---- fused Adam over packed rows (server-side G, a7) ------------------------------------
+ * torch.optim.Adam(betas=(b1,b2)) semantics, CGLGAN/2DMG/main.py:192. step[r] is incremented.
+ * rows: R rows of n floats, `ld` floats apart, for p / g / m / v alike.                      */
+int cgl_adam_rows(int R, int64_t n, int64_t ld, float* p, const float* g, float* m, float* v,
+                  int32_t* step, float lr, float beta1, float beta2, float eps,
+                  cgl_stream_t stream);
+
+/* ---- K3: aggregation over packed parameter rows -------------------------------------------
+ * cgl_mix_csr:   dst[r,:] = sum_j vals[j] * src[col[j],:]  for j in [row_ptr[r], row_ptr[r+1])
+ *   One op for FedAvg (FLGAN/MNIST/flgan.py:143-163), MD-GAN swap = permutation
+ *   (MDGAN/MNIST/mdgan.py:158-164), neighbour / group mean (ACGAN/MNIST/acgan.py:240-263,
+ *   CGLGAN/2DMG/main.py:171-179). src and dst must not overlap. Accumulation runs in column order
+ *   j, each product and sum rounded to fp32 separately (the dict loop of Cloud.run).
+ * cgl_wsum:      out[:] = sum_c w[c] * src[rows ? rows[c] : c, :]   (Cloud.run,
+ *   CGLGAN/2DMG/main.py:126-133; fedavg_aggregate, capgan.py:114)
+ * cgl_bcast_mix: dst[rows ? rows[r] : r, :] = sigma * dst[..] + (1-sigma) * g[:]   (the `segema`
+ *   mix + load_state_dict, CGLGAN/2DMG/main.py:205-208; Worker.run load, flgan.py:222-223)       */
+int cgl_mix_csr(int R, int64_t n, const int32_t* row_ptr, const int32_t* col, const float* vals,
+                const float* src, int64_t ld_src, float* dst, int64_t ld_dst, cgl_stream_t stream);
+int cgl_wsum(int C, int64_t n, const float* w, const int32_t* rows, const float* src, int64_t ld_src,
+             float* out, cgl_stream_t stream);
+int cgl_bcast_mix(int R, int64_t n, const int32_t* rows, float sigma, const float* g, float* dst,
+                  int64_t ld_dst, cgl_stream_t stream);
+
+/* ---- cross-GPU aggregation (the only collective on the path) --------------------------------
+ * One process per GPU. rank 0 calls cgl_comm_unique_id, ships the 128 bytes to the other ranks
+ * (torch.distributed broadcast), every rank calls cgl_comm_init. cgl_mix_allreduce computes the
+ * local weighted partial sum (cgl_wsum with pre-normalised weights) and all-reduces it in place
+ * over NVLink on `stream`: the Cloud / FL server aggregation when clients are sharded.          */
+int cgl_comm_unique_id(uint8_t out_id[128]);
+int cgl_comm_init(int nranks, int rank, const uint8_t id[128], cgl_comm_t* out_comm);
+int cgl_comm_destroy(cgl_comm_t comm);
+int cgl_allreduce_sum(cgl_comm_t comm, float* buf, int64_t n, cgl_stream_t stream);
+int cgl_mix_allreduce(cgl_comm_t comm, int C_local, int64_t n, const float* w_local,
+                      const int32_t* rows, const float* src, int64_t ld_src, float* out,
+                      cgl_stream_t stream);
+
+/* ---- building blocks (exported for tests and for the host-side generator step) -------------
+ * Grouped Linear over G independent groups, fp32:
+ *   fwd : y[g] = act(x[g] W[g]^T + b[g])        x [rows,in] (ldx), W [out,in], y [rows,out]
+ *   bwd : dx[g] = (dy[g] W[g]) * act'(saved[g]) (saved NULL -> no activation derivative)
+ *   wgrad: dW[g] = dy[g]^T x[g], db[g] = colsum(dy[g])
+ * W/b/dW/db live in packed rows: pointer = base + (ids ? ids[g] : g) * ld + offset.             */
+int cgl_linear_fwd(int G, int rows, int in, int out, const float* x, int64_t x_gstride,
+                   const float* wbase, int64_t ldp, const int32_t* ids, int64_t w_off, int64_t b_off,
+                   int act, float slope, float* y, int64_t y_gstride, cgl_stream_t stream);
+int cgl_linear_bwd_data(int G, int rows, int in, int out, const float* dy, int64_t dy_gstride,
+                        const float* wbase, int64_t ldp, const int32_t* ids, int64_t w_off,
+                        const float* saved, int64_t saved_gstride, int act, float slope, float* dx,
+                        int64_t dx_gstride, cgl_stream_t stream);
+int cgl_linear_wgrad(int G, int rows, int in, int out, const float* dy, int64_t dy_gstride,
+                     const float* x, int64_t x_gstride, float* gbase, int64_t ldg,
+                     const int32_t* ids, int64_t w_off, int64_t b_off, cgl_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CGL_B200_H */
