@@ -90,7 +90,7 @@ class ClientBank:
                                      abi.ptr(self.adam_v), self.ld, abi.ptr(self.step), abi.ptr(client_ids),
                                      abi.ptr(real), abi.ptr(n_real), abi.ptr(fake), abi.ptr(fake_idx), B,
                                      C.byref(self.cfg), abi.ptr(out), abi.ptr(ws), ws.numel(), _stream()))
-        self.launches += 1 + 3 * (self.desc.n_layers - 1) + 1
+        self.launches += 3 * self.desc.n_layers - 2   # bump, L-1 fwd, head, L-2 bwd-data, L-1 wgrad+Adam
         return out
 
     def g_loss_raw(self, xg, xg_idx=None, client_ids=None, need_grad=True):
@@ -108,7 +108,7 @@ class ClientBank:
         abi.check(abi.lib.cgl_g_loss(C.byref(self.desc), G, abi.ptr(self.params), self.ld, abi.ptr(client_ids),
                                      abi.ptr(xg), abi.ptr(xg_idx), B, self.cfg.loss_kind, abi.ptr(loss),
                                      abi.ptr(dxg), abi.ptr(ws), ws.numel(), _stream()))
-        self.launches += (self.desc.n_layers - 1) + 1 + (self.desc.n_layers - 1 if need_grad else 0)
+        self.launches += self.desc.n_layers + (self.desc.n_layers - 1 if need_grad else 0)
         return loss, dxg
 
     def g_loss(self, xg, xg_idx=None, client_ids=None):

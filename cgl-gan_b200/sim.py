@@ -1,0 +1,332 @@
+"""Host loops: the reference's simulations as single-threaded rounds over the engine.
+
+The reference runs one Python thread per Worker / Server / Cloud and moves tensors through queues
+(SURVEY.md 3.2-3.3). Here one `round()` advances every server and every client of this process:
+
+  MD-style (CGLGAN, CAPGAN, Mix-G, MDGAN, ACGAN): MDStyleSim
+     Server.train  CGLGAN/2DMG/main.py:225-278, capgan.py:211-262, mixed-gan.py:238-292,
+                   MDGAN/MNIST/mdgan.py:180-207, ACGAN/MNIST/acgan.py:149-179
+     Worker.train  CGLGAN/2DMG/main.py:344-375, capgan.py:316-349
+     Cloud.run     CGLGAN/2DMG/main.py:116-136 (+ the segema mix at :205-208)
+  FL-style (FLGAN): FLStyleSim
+     Worker.train  FLGAN/MNIST/flgan.py:245-270, FLGAN/2DMG/flgan.py:227-258
+     Server.run    FLGAN/MNIST/flgan.py:143-163
+
+Knob names are the reference's module-level globals (README.md:23-35).
+"""
+from dataclasses import dataclass, field
+from random import Random
+from typing import Optional
+
+import torch
+import torch.nn.functional as F
+
+from . import abi
+from .engine import ClientBank, adam_rows
+from .generators import StackedGenerator
+from .partition import assign_clients
+
+ALGOS = {
+    #  name        : (multi_head, d_arch(2d, mnist),                   loss,          d_scale, weighting)
+    "cglgan": dict(loss=abi.LOSS_BCE, d_scale=1.0, weighting="cgl"),
+    "capgan": dict(loss=abi.LOSS_CE, d_scale=0.5, weighting="cap"),
+    "capgan_copy": dict(loss=abi.LOSS_CE, d_scale=0.5, weighting="cap_copy"),
+    "mixed": dict(loss=abi.LOSS_CE, d_scale=0.5, weighting="mixed"),
+    "mdgan": dict(loss=abi.LOSS_BCE, d_scale=1.0, weighting="mean"),
+    "acgan": dict(loss=abi.LOSS_CE, d_scale=1.0, weighting="mean"),
+}
+
+
+@dataclass
+class Knobs:
+    """The reference's global knobs (CGLGAN/2DMG/main.py:30-58, mixed-gan.py:41-59)."""
+    num_workers: int = 10
+    num_servers: int = 5
+    batch_size: int = 100
+    epoch: int = 1            # local D steps per round
+    cloud_epoch: int = 1      # rounds between cloud aggregations (0: never)
+    segema: float = 0.0       # 1: fully independent servers, 0: fully shared trunk
+    E: int = 0                # rounds between neighbour-D shares (0: off, as shipped: commented out)
+    frac_workers: float = 1.0
+    iid: int = 1
+    b1: float = 0.5
+    b2: float = 0.999
+    lr_g: float = 0.0002
+    lr_d: float = 0.0002
+    img_shape: tuple = (2,)
+    cloud_mode: str = "intended"   # "as_written": the state_dict key mismatch makes Cloud a no-op
+    d_share: str = "group_mean"    # neighbour-D share flavour when E > 0: "group_mean" | "swap"
+
+
+class MDStyleSim:
+    """Server owns G, every client owns a D. One instance per process (= per GPU shard)."""
+
+    def __init__(self, algo, knobs: Knobs, part_sizes=None, device="cuda", comm=None, server_offset=0,
+                 total_data_len=None):
+        assert algo in ALGOS
+        self.algo, self.k = algo, knobs
+        spec = ALGOS[algo]
+        k = knobs
+        self.device = torch.device(device)
+        self.S = k.num_servers
+        self.N = k.num_workers // k.num_servers
+        self.C = self.S * self.N
+        self.B = k.batch_size
+        d = 1
+        for s in k.img_shape:
+            d *= s
+        self.d = d
+        two_d = d == 2
+        # generator flavour: CGLGAN -> Generator(ims, N if iid != 0 else 1) (CGLGAN/2DMG/main.py:191);
+        # mixed-gan -> MixGenerator(ims, N); the rest -> plain Generator(ims)
+        if algo == "cglgan":
+            self.n_heads = self.N if k.iid != 0 else 1
+        elif algo == "mixed":
+            self.n_heads = self.N
+        else:
+            self.n_heads = 0
+        self.multi_head = self.n_heads == self.N and self.n_heads > 0 and not (algo == "cglgan" and k.iid == 0)
+        if two_d:
+            d_arch = abi.ARCH_D_2D
+            loss = abi.LOSS_BCE            # every 2DMG script pairs BCE with the sigmoid D
+        else:
+            loss = spec["loss"]
+            d_arch = abi.ARCH_D_MNIST2 if loss == abi.LOSS_CE else abi.ARCH_D_MNIST1
+        self.loss_kind = loss
+        self.G = StackedGenerator(k.img_shape, self.S, self.n_heads, device=self.device, lr=k.lr_g, b1=k.b1, b2=k.b2)
+        self.bank = ClientBank(d_arch, self.C, self.B, device=self.device, loss_kind=loss,
+                               d_loss_scale=1.0 if two_d else spec["d_scale"], lr=k.lr_d, b1=k.b1, b2=k.b2)
+        self.weighting = spec["weighting"]
+        self.client_list, _ = assign_clients(self.C, self.S)
+        self.server_of = torch.arange(self.C, device=self.device, dtype=torch.int32) // self.N
+        # beta: client share of its server's data; A: server share of all data (CGLGAN/2DMG/main.py:184-188,117-122)
+        if part_sizes is None:
+            part_sizes = [1] * self.C
+        sizes = torch.tensor(part_sizes, dtype=torch.float32).view(self.S, self.N)
+        self.data_len = sizes.sum(1)
+        self.beta = (sizes / self.data_len.unsqueeze(1)).to(self.device)
+        tot = self.data_len.sum() if total_data_len is None else torch.tensor(float(total_data_len))
+        self.A = (self.data_len / tot).to(self.device)
+        self.Lambda = torch.zeros(self.S, device=self.device)
+        self.comm = comm                  # dist.ShardComm or None (single process)
+        self.server_offset = server_offset
+        self.t = 0                        # rounds done
+        self.last_F_max = None
+        self.swap_rd = [Random(s + server_offset + 100) for s in range(self.S)]  # Server.rd, main.py:154-155
+        self.profile = False              # bench: CUDA events around the client-step kernels
+        self._events = []
+
+    def client_step_ms(self):
+        """Mean device time per round of the client-step calls (cgl_d_step + cgl_g_loss), from the CUDA
+        events recorded while self.profile was set. Call after a synchronize."""
+        if not self._events:
+            return None
+        ms = sum(a.elapsed_time(b) for a, b in self._events) / len(self._events)
+        self._events = []
+        return ms
+
+    # ---- initialisation from reference-style modules -------------------------------------------
+    def load(self, g_modules, d_modules):
+        self.G.load_modules(g_modules)
+        self.bank.load_modules(d_modules)
+
+    # ---- one communication round ----------------------------------------------------------------
+    def round(self, real, n_real=None, z_d=None, z_g=None):
+        """real: [epoch, C, B, d] (or [C, B, d] when epoch == 1) device tensor of the clients' minibatches,
+        n_real: matching valid-row counts (None: full batches). Returns the clients' G losses [S, N]."""
+        k, S, N, B, d = self.k, self.S, self.N, self.B, self.d
+        if real.dim() == 3:
+            real = real.unsqueeze(0)
+        if n_real is not None and n_real.dim() == 1:
+            n_real = n_real.unsqueeze(0)
+        if k.cloud_epoch and self.t % k.cloud_epoch == 0:
+            self.cloud_aggregate()
+        if k.E and self.t % k.E == 0 and self.t > 0:
+            self.share_discriminators()
+        if z_d is None:
+            z_d = torch.randn(S, B, 100, device=self.device)
+        if z_g is None:
+            z_g = torch.randn(S, B, 100, device=self.device)
+        G = self.G
+        with torch.no_grad():
+            Xd = G(z_d)
+        Xg = G(z_g)
+        shared = not self.multi_head
+        if shared and self.n_heads == 1:      # CGLGAN iid==0: Generator(ims, 1), one head shared by all
+            Xd, Xg_flat = Xd.reshape(S, B, d), Xg.reshape(S, B, d)
+        elif shared:
+            Xg_flat = Xg.reshape(S, B, d)
+        else:
+            Xd, Xg_flat = Xd.reshape(S * N, B, d), Xg.reshape(S * N, B, d)
+        idx = self.server_of if shared else None
+        if self.profile:
+            ev0 = torch.cuda.Event(enable_timing=True)
+            ev0.record()
+        for e in range(real.shape[0]):
+            self.last_d_loss = self.bank.d_step(real[e], Xd, n_real=None if n_real is None else n_real[e],
+                                                fake_idx=idx)
+        loss = self.bank.g_loss(Xg_flat, xg_idx=idx).view(S, N)
+        if self.profile:
+            ev1 = torch.cuda.Event(enable_timing=True)
+            ev1.record()
+            self._events.append((ev0, ev1))
+        w = self._server_weights(loss.detach())
+        G.zero_grad()
+        if self.multi_head:
+            # heads: d(sum_i loss_i); trunk: d(sum_i w_i loss_i)  (CGLGAN/2DMG/main.py:254-269, mixed-gan.py:263-281)
+            G.trunk_scale["w"] = w.view(S, N, 1, 1)
+            loss.sum().backward()
+            G.trunk_scale["w"] = None
+        else:
+            (w * loss).sum().backward()
+        G.adam_step()
+        self.t += 1
+        return loss.detach()
+
+    def _server_weights(self, loss):
+        """Per-client weight of its G loss in the server objective; also advances Lambda."""
+        beta, Lam = self.beta, self.Lambda
+        kind = self.weighting
+        if kind == "mean":                      # MDGAN/MNIST/mdgan.py:203, ACGAN/MNIST/acgan.py:173
+            self.last_F_max = loss.mean(1)
+            return torch.full_like(loss, 1.0 / self.N)
+        if kind == "cgl":                       # CGLGAN/2DMG/main.py:261-274
+            gamma = F.softmax(Lam.unsqueeze(1) * loss, dim=1)
+            F_beta = (beta * loss).sum(1)
+            F_gamma = (gamma * loss).sum(1)
+            self.last_F_max = (F_beta + F_gamma) / 2
+            grad = (loss * loss * gamma).sum(1) - (loss * gamma * F_gamma.unsqueeze(1)).sum(1)
+            self.Lambda = Lam + 10 * grad
+            return (beta + gamma) / 2
+        if kind == "cap":                       # capgan.py:247-249
+            alpha = F.softmax(Lam.unsqueeze(1) * loss, dim=1)
+            alpha = F.softmax(alpha * beta, dim=1)
+        elif kind == "cap_copy":                # CAPGAN/MNIST/capgan.py:241-243
+            gamma = F.softmax(Lam.unsqueeze(1) * loss, dim=1)
+            alpha = F.softmax(beta * gamma, dim=1)
+        elif kind == "mixed":                   # mixed-gan.py:276-277
+            alpha = F.softmax(beta * Lam.unsqueeze(1) * loss, dim=1)
+        else:
+            raise ValueError(kind)
+        self.last_F_max = (alpha * loss).sum(1) - 0.001 * Lam
+        # opti_L = SGD([Lambda], lr=0.1); dF_max/dLambda = -0.001 (capgan.py:160,250,259)
+        self.Lambda = Lam.add(torch.full_like(Lam, -0.001), alpha=-0.1)
+        return alpha
+
+    # ---- aggregation ------------------------------------------------------------------------------
+    def cloud_aggregate(self):
+        """Cloud.run + the receiving half of Server.run (CGLGAN/2DMG/main.py:124-136,201-208):
+        p = sum_s A[s] * trunk_s ; trunk_s <- segema*trunk_s + (1-segema)*p, BN running stats included
+        (copy_parameters keeps every non-0-dim state_dict entry). capgan: whole generator, parameters only
+        (fedlab serialize_model, capgan.py:170-175)."""
+        k = self.k
+        if self.algo in ("mdgan", "acgan"):
+            return  # these scripts have no Cloud
+        if self.algo in ("cglgan", "mixed") and k.cloud_mode == "as_written":
+            return  # keys '0.weight' never match 'model.0.weight': load_state_dict(strict=False) loads nothing
+        with torch.no_grad():
+            bank = self.G.trunk    # cglgan / mixed: net_g.model; capgan: the whole (single-path) generator
+            assert bank.rows == self.S
+            bufs = [(bank.params.detach(), bank.lay.ld)]
+            if bank.lay.n_stats and self.algo in ("cglgan", "mixed"):
+                bufs.append((bank.stats, bank.lay.ld_stats))   # dict form carries running_mean / running_var
+            for buf, ld in bufs:
+                g = torch.empty(ld, device=self.device)
+                _wsum(self.A, None, buf, ld, g, self.comm)
+                _bcast(None, k.segema, g, buf, ld, rows_n=bank.rows)
+
+    def share_discriminators(self):
+        """Neighbour-D share every E rounds (commented out in the shipped scripts, README.md:26):
+        "group_mean": every client of a server ends with the mean D of that server's clients
+        (ACGAN/MNIST/acgan.py:240-263 fixed point == CGLGAN/2DMG/main.py:171-179);
+        "swap": the server shuffles its clients' Ds (MDGAN/MNIST/mdgan.py:158-164,258-262)."""
+        C, N = self.C, self.N
+        M = torch.zeros(C, C)
+        for s, cl in enumerate(self.client_list):
+            if self.k.d_share == "swap":
+                order = list(range(len(cl)))
+                self.swap_rd[s].shuffle(order)
+                for j, c in enumerate(cl):
+                    M[c, cl[order[j]]] = 1.0
+            else:
+                for c in cl:
+                    M[c, cl] = 1.0 / len(cl)
+        self.bank.mix(M)
+
+
+def _wsum(w, rows, buf, ld, out, comm):
+    from .engine import _stream
+    import ctypes as C
+    w = w.contiguous()
+    if comm is None:
+        abi.check(abi.lib.cgl_wsum(w.numel(), ld, abi.ptr(w), abi.ptr(rows), abi.ptr(buf), ld, abi.ptr(out), _stream()))
+    else:
+        abi.check(abi.lib.cgl_mix_allreduce(comm.handle, w.numel(), ld, abi.ptr(w), abi.ptr(rows), abi.ptr(buf), ld,
+                                            abi.ptr(out), _stream()))
+
+
+def _bcast(rows, sigma, g, buf, ld, rows_n=None):
+    from .engine import _stream
+    R = rows.numel() if rows is not None else rows_n
+    abi.check(abi.lib.cgl_bcast_mix(R, ld, abi.ptr(rows), float(sigma), abi.ptr(g), abi.ptr(buf), ld, _stream()))
+
+
+class FLStyleSim:
+    """FL-GAN: every client owns G and D; the server averages both every round.
+    Worker.run/train FLGAN/MNIST/flgan.py:211-270, Server.run :134-163. Adam state stays with the client and
+    is neither reset nor averaged when the parameters are overwritten (optimizers built once, :217-218)."""
+
+    def __init__(self, knobs: Knobs, device="cuda", comm=None, weights=None):
+        k = knobs
+        self.k = k
+        self.device = torch.device(device)
+        self.C, self.B = k.num_workers, k.batch_size
+        d = 1
+        for s in k.img_shape:
+            d *= s
+        self.d = d
+        self.G = StackedGenerator(k.img_shape, self.C, 0, device=self.device, lr=k.lr_g, b1=k.b1, b2=k.b2)
+        self.bank = ClientBank(abi.ARCH_D_2D if d == 2 else abi.ARCH_D_MNIST1, self.C, self.B, device=self.device,
+                               loss_kind=abi.LOSS_BCE, lr=k.lr_d, b1=k.b1, b2=k.b2)
+        n_total = k.num_workers if comm is None else k.num_workers * comm.world
+        # p[key] += paras[key] / len(client_list)  (flgan.py:151-158); weights override = FeGAN's softmax(sk)
+        self.w = (torch.full((self.C,), 1.0 / n_total) if weights is None else
+                  torch.as_tensor(weights, dtype=torch.float32)).to(self.device)
+        self.comm = comm
+        self.t = 0
+
+    def load_global(self, g_module, d_module):
+        """Round-0 state: the server's initial net_g / net_d copied to every client (flgan.py:139-146)."""
+        self.G.load_modules([g_module] * self.C)
+        self.bank.load_modules([d_module] * self.C)
+
+    def local_minibatch(self, real, n_real=None, z_d=None, z_g=None):
+        """One D step + one G step on every client (flgan.py:251-269)."""
+        C, B = self.C, self.B
+        if z_d is None:
+            z_d = torch.randn(C, B, 100, device=self.device)
+        if z_g is None:
+            z_g = torch.randn(C, B, 100, device=self.device)
+        G = self.G
+        with torch.no_grad():   # the G grads D_loss.backward() leaves behind are zeroed at flgan.py:264
+            Xd = G(z_d)
+        d_loss = self.bank.d_step(real, Xd.reshape(C, B, self.d), n_real=n_real)
+        G.zero_grad()
+        Xg = G(z_g)
+        g_loss = self.bank.g_loss(Xg.reshape(C, B, self.d))
+        g_loss.sum().backward()
+        G.adam_step()
+        return d_loss, g_loss.detach()
+
+    def aggregate(self):
+        """Server.run: uniform (or weighted) average of every client's G and D, loaded back into every
+        client (flgan.py:143-163,220-223). BN running stats take part (dict form, copy_parameters)."""
+        with torch.no_grad():
+            bufs = [(self.bank.params, self.bank.ld), (self.G.trunk.params.detach(), self.G.trunk.lay.ld)]
+            if self.G.trunk.lay.n_stats:
+                bufs.append((self.G.trunk.stats, self.G.trunk.lay.ld_stats))
+            for buf, ld in bufs:
+                g = torch.empty(ld, device=self.device)
+                _wsum(self.w, None, buf, ld, g, self.comm)
+                _bcast(None, 0.0, g, buf, ld, rows_n=self.C)
+        self.t += 1

@@ -5,7 +5,7 @@ import random
 import pytest
 import torch
 
-from helpers import D_IN, make_batches, make_ds, rel_err, osteps
+from helpers import D_IN, assert_params_close, make_batches, make_ds, rel_err, rel_l2, osteps
 
 pytestmark = pytest.mark.gpu
 
@@ -36,6 +36,15 @@ def test_d_step_and_g_loss_match_oracle(lib, arch, scale, steps):
         real_pad = real.clone()
         for g in range(G):
             real_pad[g, n_real[g]:] = 0
+        if it == 0:
+            # generator-loss path alone, on identical parameters: tight fp32 agreement
+            l_pre, dx_pre = bank.g_loss_raw(xg.cuda())
+            for g in range(G):
+                x = xg[g].clone().requires_grad_(True)
+                l_ref = osteps.worker_g_loss(nets[g], loss, kind, x, B)
+                l_ref.backward()
+                assert abs(l_pre[g].item() - l_ref.item()) < 1e-5, (g, l_pre[g].item(), l_ref.item())
+                assert rel_err(dx_pre[g], x.grad) < 1e-5, (g, rel_err(dx_pre[g], x.grad))
         d_gpu = bank.d_step(real_pad.cuda(), fake.cuda(), n_real=n_real)
         xg_dev = xg.cuda().requires_grad_(True)
         l_gpu = bank.g_loss(xg_dev)
@@ -47,17 +56,14 @@ def test_d_step_and_g_loss_match_oracle(lib, arch, scale, steps):
             l_ref.backward()
             assert abs(d_gpu[g].item() - d_ref.item()) < LOSS_TOL, (it, g, d_gpu[g].item(), d_ref.item())
             assert abs(l_gpu[g].item() - l_ref.item()) < LOSS_TOL, (it, g)
-            assert rel_err(xg_dev.grad[g], x.grad) < 1e-4, (it, g, rel_err(xg_dev.grad[g], x.grad))
+            # after an Adam step the two D's differ at the ill-conditioned elements (see assert_params_close)
+            assert rel_l2(xg_dev.grad[g], x.grad) < 1e-3, (it, g, rel_l2(xg_dev.grad[g], x.grad))
     for g in range(G):
-        ref = torch.cat([p.detach().reshape(-1) for p in nets[g].parameters()])
-        e = rel_err(bank.rows()[g], ref)
-        assert e < PARAM_TOL, (g, e)
-        # layer-wise too (a small layer must not hide behind a large one)
+        # layer-wise (a small layer must not hide behind a large one)
         off = 0
         for p in nets[g].parameters():
             n = p.numel()
-            e = rel_err(bank.rows()[g, off:off + n], p.reshape(-1))
-            assert e < PARAM_TOL, (g, off, e)
+            assert_params_close(bank.rows()[g, off:off + n], p.reshape(-1), steps=steps, tag=(g, off))
             off += n
     assert bank.step.tolist() == [steps] * G
 
@@ -78,7 +84,7 @@ def test_d_step_indexed_clients_and_shared_fake(lib):
         opt = osteps.make_adam(nets[c].parameters())
         osteps.worker_d_step(nets[c], opt, loss, 0, real[j], fake[fake_idx[j]], B)
         ref = torch.cat([p.detach().reshape(-1) for p in nets[c].parameters()])
-        assert rel_err(bank.rows()[c], ref) < PARAM_TOL
+        assert_params_close(bank.rows()[c], ref, tag=c)
     for c in (0, 2, 5):   # untouched rows stay bit-identical
         assert torch.equal(bank.rows()[c], before[c])
     assert bank.step.tolist() == [0, 1, 0, 1, 1, 0]
@@ -92,7 +98,7 @@ def test_d_step_indexed_clients_and_shared_fake(lib):
     for j, c in enumerate(ids.tolist()):
         tot = tot + w[j] * osteps.worker_g_loss(nets[c], loss, 0, x[fake_idx[j]], B)
     tot.backward()
-    assert rel_err(xg_dev.grad, x.grad) < 1e-4
+    assert rel_l2(xg_dev.grad, x.grad) < 1e-3
 
 
 def test_linear_blocks_against_torch(lib):

@@ -1,0 +1,109 @@
+"""Whole-round parity on the GPU: cgl_gan_b200.sim host loops (engine kernels) against oracle.rounds
+(serial CPU restatement of Server.run / Worker.train / Cloud.run) on identical injected inputs."""
+import pytest
+import torch
+
+from helpers import assert_params_close, rel_err, rel_l2
+from oracle.rounds import OracleFL, OracleMD
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    # algo, img_shape, workers, servers, iid, segema, epoch, rounds
+    ("cglgan", (2,), 10, 5, 1, 0.0, 1, 3),          # BASELINE config[0]: CGLGAN 2DMG, repo-default topology
+    ("cglgan", (2,), 4, 2, 0, 0.0, 2, 2),           # iid==0: Generator(ims, 1), shared Xd/Xg, epoch=2
+    ("cglgan", (1, 28, 28), 4, 2, 1, 0.3, 1, 2),    # BASELINE config[1]: CGLGAN MNIST multi-head + segema mix
+    ("capgan", (1, 28, 28), 4, 2, 1, 0.0, 1, 2),
+    ("capgan_copy", (1, 28, 28), 4, 2, 1, 0.0, 1, 2),
+    ("mixed", (1, 28, 28), 4, 2, 1, 0.5, 1, 2),     # BASELINE config[2]: CAPGAN + Mix-G
+    ("mdgan", (1, 28, 28), 3, 1, 1, 0.0, 1, 2),     # BASELINE config[3]
+    ("acgan", (1, 28, 28), 4, 2, 1, 0.0, 1, 2),
+]
+
+
+def _inputs(C, S, B, d, epoch, seed):
+    g = torch.Generator().manual_seed(seed)
+    real = torch.tanh(torch.randn(epoch, C, B, d, generator=g))
+    n_real = torch.full((epoch, C), B, dtype=torch.int32)
+    n_real[:, 0] = 41          # a short last DataLoader batch (partition of 29941 samples -> 41)
+    for e in range(epoch):
+        real[e, 0, 41:] = 0
+    z_d = torch.randn(S, B, 100, generator=g)
+    z_g = torch.randn(S, B, 100, generator=g)
+    return real, n_real, z_d, z_g
+
+
+@pytest.mark.parametrize("algo,shape,W,S,iid,segema,epoch,rounds", CASES)
+def test_md_round_matches_oracle(lib, algo, shape, W, S, iid, segema, epoch, rounds):
+    from cgl_gan_b200.sim import Knobs, MDStyleSim
+    torch.manual_seed(20211212)
+    B = 100
+    d = 1
+    for s in shape:
+        d *= s
+    sizes = [1000 + 137 * i for i in range(W)]
+    orc = OracleMD(algo, W, S, B, shape, iid=iid, part_sizes=sizes, segema=segema, weights_init=(algo == "mixed"))
+    k = Knobs(num_workers=W, num_servers=S, batch_size=B, epoch=epoch, segema=segema, iid=iid, img_shape=shape)
+    sim = MDStyleSim(algo, k, part_sizes=sizes)
+    sim.load(orc.net_g, orc.net_d)
+    for r in range(rounds):
+        real, n_real, z_d, z_g = _inputs(W, S, B, d, epoch, seed=50 + r)
+        l_ref = orc.round(real, n_real, z_d, z_g)
+        l_gpu = sim.round(real.cuda(), n_real.cuda(), z_d.cuda(), z_g.cuda())
+        assert (l_gpu.cpu() - l_ref).abs().max() < 1e-4, (r, l_gpu.cpu(), l_ref)       # loss curves within 1e-4
+        F_ref = torch.stack([torch.as_tensor(f).reshape(()) for f in orc.F_max])
+        assert (sim.last_F_max.cpu() - F_ref).abs().max() < 1e-4
+    Lam_ref = torch.stack([L.detach().reshape(()) for L in orc.Lambda])
+    assert (sim.Lambda.cpu() - Lam_ref).abs().max() < 1e-4 * max(1.0, Lam_ref.abs().max().item())
+    steps = rounds * epoch
+    for c in range(W):
+        ref = torch.cat([p.detach().reshape(-1) for p in orc.net_d[c].parameters()])
+        assert_params_close(sim.bank.rows()[c], ref, steps=steps, tag=("D", c))
+    for s in range(S):
+        m = sim.G.make_module()
+        sim.G.store_module(s, m)
+        for (k1, v1), (k2, v2) in zip(m.state_dict().items(), orc.net_g[s].state_dict().items()):
+            assert k1 == k2
+            if v1.dim():
+                if "running" in k1:
+                    assert rel_err(v1, v2) < 1e-5, (s, k1)
+                else:
+                    assert_params_close(v1, v2, steps=rounds, tag=("G", s, k1))
+
+
+@pytest.mark.parametrize("shape", [(2,), (1, 28, 28)])
+def test_fl_round_matches_oracle(lib, shape):
+    """FL-GAN (BASELINE config[3]): local D+G minibatches on every client, then the uniform average."""
+    from cgl_gan_b200.sim import FLStyleSim, Knobs
+    torch.manual_seed(7)
+    C, B = 3, 100
+    d = 1
+    for s in shape:
+        d *= s
+    orc = OracleFL(C, B, shape)
+    orc.load_global()
+    sim = FLStyleSim(Knobs(num_workers=C, num_servers=1, batch_size=B, img_shape=shape))
+    sim.load_global(orc.srv_g, orc.srv_d)
+    g = torch.Generator().manual_seed(1)
+    for r in range(2):
+        for mb in range(2):
+            real = torch.tanh(torch.randn(C, B, d, generator=g))
+            n_real = torch.tensor([B, 60, B], dtype=torch.int32)
+            real[1, 60:] = 0
+            z_d, z_g = torch.randn(C, B, 100, generator=g), torch.randn(C, B, 100, generator=g)
+            dl_ref, gl_ref = orc.local_minibatch(real, n_real, z_d, z_g)
+            dl, gl = sim.local_minibatch(real.cuda(), n_real.cuda(), z_d.cuda(), z_g.cuda())
+            assert (dl.cpu() - dl_ref).abs().max() < 1e-4 and (gl.cpu() - gl_ref).abs().max() < 1e-4
+        orc.aggregate()
+        sim.aggregate()
+    for c in range(C):
+        ref = torch.cat([p.detach().reshape(-1) for p in orc.net_d[c].parameters()])
+        assert_params_close(sim.bank.rows()[c], ref, steps=4, tag=("D", c))
+        m = sim.G.make_module()
+        sim.G.store_module(c, m)
+        for (k1, v1), (k2, v2) in zip(m.state_dict().items(), orc.net_g[c].state_dict().items()):
+            if v1.dim():
+                if "running" in k1:
+                    assert rel_err(v1, v2) < 1e-5, (c, k1)
+                else:
+                    assert_params_close(v1, v2, steps=4, tag=("G", c, k1))
