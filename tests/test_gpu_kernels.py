@@ -5,7 +5,7 @@ import random
 import pytest
 import torch
 
-from helpers import D_IN, assert_params_close, make_batches, make_ds, rel_err, rel_l2, osteps
+from helpers import D_IN, assert_params_close, assert_rows_close, make_batches, make_ds, rel_err, rel_l2, osteps
 
 pytestmark = pytest.mark.gpu
 
@@ -44,7 +44,7 @@ def test_d_step_and_g_loss_match_oracle(lib, arch, scale, steps):
                 l_ref = osteps.worker_g_loss(nets[g], loss, kind, x, B)
                 l_ref.backward()
                 assert abs(l_pre[g].item() - l_ref.item()) < 1e-5, (g, l_pre[g].item(), l_ref.item())
-                assert rel_err(dx_pre[g], x.grad) < 1e-5, (g, rel_err(dx_pre[g], x.grad))
+                assert_rows_close(dx_pre[g], x.grad, tag=g)
         d_gpu = bank.d_step(real_pad.cuda(), fake.cuda(), n_real=n_real)
         xg_dev = xg.cuda().requires_grad_(True)
         l_gpu = bank.g_loss(xg_dev)
@@ -63,7 +63,7 @@ def test_d_step_and_g_loss_match_oracle(lib, arch, scale, steps):
         off = 0
         for p in nets[g].parameters():
             n = p.numel()
-            assert_params_close(bank.rows()[g, off:off + n], p.reshape(-1), steps=steps, tag=(g, off))
+            assert_params_close(bank.rows()[g, off:off + n], p.reshape(-1), steps=steps, tag=(g, off), strict=(steps == 1))
             off += n
     assert bank.step.tolist() == [steps] * G
 
