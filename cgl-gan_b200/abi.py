@@ -9,6 +9,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libcgl_b200.so")
 MAX_LAYERS = 8
 ACT_NONE, ACT_LRELU, ACT_TANH, ACT_SIGMOID = 0, 1, 2, 3
 LOSS_BCE, LOSS_CE, LOSS_MSE = 0, 1, 2
+GEMM_AUTO, GEMM_FFMA, GEMM_TC = 0, 1, 2
 (ARCH_D_2D, ARCH_D_MNIST1, ARCH_D_MNIST2, ARCH_D_MNIST_LS, ARCH_G_2D_MD, ARCH_G_MNIST,
  ARCH_G_2D_TRUNK, ARCH_G_2D_HEAD, ARCH_G_MNIST_TRUNK, ARCH_G_MNIST_HEAD) = range(10)
 
@@ -67,6 +68,8 @@ lib.cgl_comm_init.argtypes = [_i32, _i32, _p, C.POINTER(_p)]
 lib.cgl_comm_destroy.argtypes = [_p]
 lib.cgl_allreduce_sum.argtypes = [_p, _p, _i64, _p]
 lib.cgl_mix_allreduce.argtypes = [_p, _i32, _i64, _p, _p, _p, _i64, _p, _p]
+lib.cgl_set_gemm_mode.argtypes = [_i32]
+lib.cgl_get_gemm_mode.restype = C.c_int
 lib.cgl_linear_fwd.argtypes = [_i32, _i32, _i32, _i32, _p, _i64, _p, _i64, _p, _i64, _i64, _i32, _f32, _p, _i64, _p]
 lib.cgl_linear_bwd_data.argtypes = [_i32, _i32, _i32, _i32, _p, _i64, _p, _i64, _p, _i64, _p, _i64, _i32, _f32,
                                     _p, _i64, _p]
@@ -75,7 +78,7 @@ lib.cgl_linear_wgrad.argtypes = [_i32, _i32, _i32, _i32, _p, _i64, _p, _i64, _p,
 for _name in ("cgl_arch_describe", "cgl_mlp_layout_of", "cgl_d_step", "cgl_g_loss", "cgl_dxg_reduce",
               "cgl_adam_rows", "cgl_mix_csr", "cgl_wsum", "cgl_bcast_mix", "cgl_comm_unique_id",
               "cgl_comm_init", "cgl_comm_destroy", "cgl_allreduce_sum", "cgl_mix_allreduce",
-              "cgl_linear_fwd", "cgl_linear_bwd_data", "cgl_linear_wgrad"):
+              "cgl_linear_fwd", "cgl_linear_bwd_data", "cgl_linear_wgrad", "cgl_set_gemm_mode"):
     getattr(lib, _name).restype = C.c_int
 
 

@@ -1,9 +1,11 @@
 // dstep.cu -- the per-client discriminator step and generator-loss evaluation (K1/K2).
 // Reference: Worker.train, CGLGAN/2DMG/main.py:344-375; capgan.py:316-349; MDGAN/MNIST/mdgan.py:266-297.
-#include "gemm.cuh"
-#include "builders.cuh"
+#include "linear.cuh"
 
 namespace cgl {
+
+static int g_gemm_mode = GEMM_AUTO;
+int gemm_mode() { return g_gemm_mode; }
 
 // ---------------------------------------------------------------------------------------------
 // Head kernel: last Linear (H -> nout, nout <= 2) + output activation + loss + its backward.
@@ -236,9 +238,8 @@ static int forward_hidden(const cgl_mlp_desc* a, const cgl_mlp_layout& lay, int 
                           const float* params, long long ldp, const int* ids, Workspace& w, cudaStream_t st) {
   for (int l = 0; l + 1 < a->n_layers; ++l) {
     RowMap A = (l == 0) ? X : single_rows(w.H[l], (long long)rows * a->dims[l], nullptr, a->dims[l]);
-    GemmParams p = fwd_params(rows, a->dims[l], a->dims[l + 1], A, params, ldp, ids, lay.w_off[l], lay.b_off[l],
-                              a->act[l], a->lrelu_slope, w.H[l + 1], (long long)rows * a->dims[l + 1]);
-    CGL_CHECK_CUDA((launch_grouped_gemm<true, true, EPI_FWD>(p, G, st)));
+    CGL_CHECK_CUDA(run_linear_fwd(G, rows, a->dims[l], a->dims[l + 1], A, params, ldp, ids, lay.w_off[l], lay.b_off[l],
+                                  a->act[l], a->lrelu_slope, w.H[l + 1], (long long)rows * a->dims[l + 1], st));
   }
   return CGL_OK;
 }
@@ -322,17 +323,14 @@ extern "C" int cgl_d_step(const cgl_mlp_desc* arch, int G, float* params, float*
   for (int l = L - 2; l >= 0; --l) {
     const int in = arch->dims[l], out = arch->dims[l + 1];
     if (l > 0) {
-      GemmParams p = bwd_data_params(rows, in, out, w.dZ[l + 1], (long long)rows * out, params, ldp, client_ids,
-                                     lay.w_off[l], w.H[l], (long long)rows * in, arch->act[l - 1], arch->lrelu_slope,
-                                     w.dZ[l], (long long)rows * in);
-      CGL_CHECK_CUDA((launch_grouped_gemm<true, false, EPI_BWD_DATA>(p, G, st)));
+      CGL_CHECK_CUDA(run_linear_bwd_data(G, rows, in, out, w.dZ[l + 1], (long long)rows * out, params, ldp, client_ids,
+                                         lay.w_off[l], w.H[l], (long long)rows * in, arch->act[l - 1],
+                                         arch->lrelu_slope, w.dZ[l], (long long)rows * in, st));
     }
     RowMap Xin = (l == 0) ? X : single_rows(w.H[l], (long long)rows * in, nullptr, in);
-    GemmParams p = wgrad_params(rows, in, out, w.dZ[l + 1], (long long)rows * out, Xin, params, ldp, client_ids,
-                                lay.w_off[l], lay.b_off[l]);
-    p.adam_m = adam_m; p.adam_v = adam_v; p.step = step;
-    p.lr = cfg->lr; p.b1 = cfg->beta1; p.b2 = cfg->beta2; p.eps = cfg->eps;
-    CGL_CHECK_CUDA((launch_grouped_gemm<false, false, EPI_ADAM>(p, G, st)));
+    const AdamArgs ad = {adam_m, adam_v, step, cfg->lr, cfg->beta1, cfg->beta2, cfg->eps};
+    CGL_CHECK_CUDA(run_linear_wgrad(G, rows, in, out, w.dZ[l + 1], (long long)rows * out, Xin, params, ldp, client_ids,
+                                    lay.w_off[l], lay.b_off[l], &ad, st));
   }
   return CGL_OK;
 }
@@ -370,18 +368,23 @@ extern "C" int cgl_g_loss(const cgl_mlp_desc* arch, int G, const float* params, 
   for (int l = L - 2; l >= 0; --l) {
     const int in = arch->dims[l], out = arch->dims[l + 1];
     if (l > 0) {
-      GemmParams p = bwd_data_params(B, in, out, w.dZ[l + 1], (long long)B * out, params, ldp, client_ids,
-                                     lay.w_off[l], w.H[l], (long long)B * in, arch->act[l - 1], arch->lrelu_slope,
-                                     w.dZ[l], (long long)B * in);
-      CGL_CHECK_CUDA((launch_grouped_gemm<true, false, EPI_BWD_DATA>(p, G, st)));
+      CGL_CHECK_CUDA(run_linear_bwd_data(G, B, in, out, w.dZ[l + 1], (long long)B * out, params, ldp, client_ids,
+                                         lay.w_off[l], w.H[l], (long long)B * in, arch->act[l - 1], arch->lrelu_slope,
+                                         w.dZ[l], (long long)B * in, st));
     } else {
-      GemmParams p = bwd_data_params(B, in, out, w.dZ[1], (long long)B * out, params, ldp, client_ids, lay.w_off[0],
-                                     nullptr, 0, CGL_ACT_NONE, 0.f, out_dxg, (long long)B * in);
-      CGL_CHECK_CUDA((launch_grouped_gemm<true, false, EPI_STORE>(p, G, st)));
+      CGL_CHECK_CUDA(run_linear_bwd_data(G, B, in, out, w.dZ[1], (long long)B * out, params, ldp, client_ids,
+                                         lay.w_off[0], nullptr, 0, CGL_ACT_NONE, 0.f, out_dxg, (long long)B * in, st));
     }
   }
   return CGL_OK;
 }
+
+extern "C" int cgl_set_gemm_mode(int mode) {
+  CGL_REQUIRE(mode == GEMM_AUTO || mode == GEMM_FFMA || mode == GEMM_TC, "gemm mode must be 0 (auto), 1 (FFMA) or 2 (tcgen05)");
+  g_gemm_mode = mode;
+  return CGL_OK;
+}
+extern "C" int cgl_get_gemm_mode(void) { return g_gemm_mode; }
 
 // ---- building blocks ------------------------------------------------------------------------
 extern "C" int cgl_linear_fwd(int G, int rows, int in, int out, const float* x, int64_t x_gstride, const float* wbase,
@@ -390,8 +393,8 @@ extern "C" int cgl_linear_fwd(int G, int rows, int in, int out, const float* x, 
   CGL_REQUIRE(G >= 0 && G <= 65535 && rows > 0 && in > 0 && out > 0, "bad shape");
   CGL_REQUIRE(x && wbase && y, "NULL tensor pointer");
   RowMap X = single_rows(x, x_gstride, nullptr, in);
-  GemmParams p = fwd_params(rows, in, out, X, wbase, ldp, ids, w_off, b_off, act, slope, y, y_gstride);
-  CGL_CHECK_CUDA((launch_grouped_gemm<true, true, EPI_FWD>(p, G, (cudaStream_t)stream)));
+  CGL_CHECK_CUDA(run_linear_fwd(G, rows, in, out, X, wbase, ldp, ids, w_off, b_off, act, slope, y, y_gstride,
+                                (cudaStream_t)stream));
   return CGL_OK;
 }
 
@@ -401,13 +404,8 @@ extern "C" int cgl_linear_bwd_data(int G, int rows, int in, int out, const float
                                    int64_t dx_gstride, cgl_stream_t stream) {
   CGL_REQUIRE(G >= 0 && G <= 65535 && rows > 0 && in > 0 && out > 0, "bad shape");
   CGL_REQUIRE(dy && wbase && dx, "NULL tensor pointer");
-  GemmParams p = bwd_data_params(rows, in, out, dy, dy_gstride, wbase, ldp, ids, w_off, saved, saved_gstride, act,
-                                 slope, dx, dx_gstride);
-  if (saved) {
-    CGL_CHECK_CUDA((launch_grouped_gemm<true, false, EPI_BWD_DATA>(p, G, (cudaStream_t)stream)));
-  } else {
-    CGL_CHECK_CUDA((launch_grouped_gemm<true, false, EPI_STORE>(p, G, (cudaStream_t)stream)));
-  }
+  CGL_CHECK_CUDA(run_linear_bwd_data(G, rows, in, out, dy, dy_gstride, wbase, ldp, ids, w_off, saved, saved_gstride, act,
+                                     slope, dx, dx_gstride, (cudaStream_t)stream));
   return CGL_OK;
 }
 
@@ -417,7 +415,7 @@ extern "C" int cgl_linear_wgrad(int G, int rows, int in, int out, const float* d
   CGL_REQUIRE(G >= 0 && G <= 65535 && rows > 0 && in > 0 && out > 0, "bad shape");
   CGL_REQUIRE(dy && x && gbase, "NULL tensor pointer");
   RowMap X = single_rows(x, x_gstride, nullptr, in);
-  GemmParams p = wgrad_params(rows, in, out, dy, dy_gstride, X, gbase, ldg, ids, w_off, b_off);
-  CGL_CHECK_CUDA((launch_grouped_gemm<false, false, EPI_STORE>(p, G, (cudaStream_t)stream)));
+  CGL_CHECK_CUDA(run_linear_wgrad(G, rows, in, out, dy, dy_gstride, X, gbase, ldg, ids, w_off, b_off, nullptr,
+                                  (cudaStream_t)stream));
   return CGL_OK;
 }

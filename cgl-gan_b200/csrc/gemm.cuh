@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) grouped_gemm_kernel(const GemmPa
 
   float ra[8], rb[8];
   const bool want_bias = (EPI == EPI_ADAM || EPI == EPI_STORE) && blockIdx.x == 0 &&
-                         (EPI == EPI_ADAM || p.dbias_off >= 0);
+                         (EPI == EPI_ADAM ? p.bias_off >= 0 : p.dbias_off >= 0);
   float bsum = 0.f;
 
   const int nk = (p.K + BK - 1) / BK;

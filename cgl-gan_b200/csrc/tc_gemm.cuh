@@ -1,0 +1,378 @@
+// tc_gemm.cuh -- grouped GEMM on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM)
+// with fp32-grade results through the 3xTF32 split (K2 of SURVEY.md section 2).
+//
+//   D[g][m][n] = sum_k A[g](m,k) * B[g](n,k)        one group g = one simulated client / edge server
+//
+// Orientation: the TMEM lane (= MMA M) dimension is always the dimension that is CONTIGUOUS in the
+// output, so that the epilogue's 32 lanes of a warp touch 128 consecutive bytes:
+//   forward   y [row][out]  : m = out feature, n = batch row,   k = in feature   (A = W  K-major, B = x  K-major)
+//   data grad dx[row][in]   : m = in feature,  n = batch row,   k = out feature  (A = W  MN-major, B = dy K-major)
+//   weight    W [out][in]   : m = in feature,  n = out feature, k = batch row    (A = x  MN-major, B = dy MN-major)
+// The batch (200 = real|fake rows, or 100) is never the M dimension: M is tiled by 128 and the layer
+// widths 784/512/256/1024 fill it, while N takes any multiple of 16 up to 256 (200 -> 208, 100 -> 112).
+//
+// Precision: the reference is strict fp32 (torch default, allow_tf32 = False). Each fp32 operand x is
+// split in registers into hi = rna_tf32(x), lo = rna_tf32(x - hi); three MMAs accumulate
+// lo*hi + hi*lo + hi*hi in the fp32 TMEM accumulator (the dropped lo*lo term is ~2^-22 relative).
+// Because the split needs a register pass anyway, operands are staged global -> registers -> shared
+// (whole 64/128-byte row segments, written straight into the canonical UMMA shared-memory layouts,
+// conflict-free) instead of by TMA; ragged / concatenated / index-selected row sources
+// (RowMap) come for free.
+//
+// Pipeline per CTA (256 threads, 128 x BN output tile, BK = 32):
+//   all threads: LDG next k-block -> registers | split -> STS stage s | fence.proxy.async | barrier
+//   thread 0   : 12 tcgen05.mma (4 k-steps x 3 split products) on stage s, tcgen05.commit -> empty[s]
+//   two stages; the commit mbarrier releases a stage for overwriting. Epilogue: tcgen05.ld 32x32b.x16,
+//   fused bias+activation / activation derivative / Adam, coalesced stores.
+#pragma once
+#include "gemm.cuh"
+
+namespace cgl {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 32;
+constexpr int TC_STAGES = 2;
+constexpr int TC_THREADS = 256;
+constexpr int TC_MAX_BN = 256;
+
+// ---- PTX wrappers ----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  unsigned long long spins = 0;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!ok && ++spins > (1ull << 26)) __trap();  // a lost arrival must fail loudly, not hang the GPU
+  } while (!ok);
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {  // one full warp
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {  // the allocating warp
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], kind::tf32 (K = 8 per instruction)
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier once every tcgen05.mma issued so far by this thread has completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// 32 lanes x 16 consecutive fp32 columns: thread i of the warp gets lane (base + i)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ float rna_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor: start >> 4 in [0,14), leading byte
+// offset >> 4 in [16,30), stride byte offset >> 4 in [32,46), version 1 in [46,48), layout type in
+// [61,64): 0 = SWIZZLE_NONE, 1 = SWIZZLE_128B_BASE32B -- the only layout tf32 accepts MN-major).
+constexpr uint32_t UMMA_LAYOUT_NONE = 0, UMMA_LAYOUT_SW128_BASE32B = 1;
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+  uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= 1ull << 46;
+  d |= (uint64_t)layout << 61;
+  return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, majors, N >> 3, M >> 4.
+__host__ __device__ inline uint32_t umma_idesc_tf32(bool a_mn_major, bool b_mn_major, int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+}
+
+// ---- operand staging --------------------------------------------------------------------------
+// A staged tile is T (= 128, or BN rounded up to 32) lines of the M/N dimension by TC_BK = 32 of K, as
+// hi and lo copies. One warp-wide float4 access covers a "patch" whose 32 float4s land in 512
+// consecutive bytes of shared memory (conflict-free) and read whole 64/128-byte row segments.
+//   K-major  (k contiguous in global; lines = m/n), no swizzle, core matrix = 8 lines x 16 B:
+//       byte(t, k) = (t/8)*1024 + (k/4)*128 + (t%8)*16 + (k%4)*4          LBO = 128 (next 4 k), SBO = 1024 (next 8 t)
+//       patch p = 8 lines x 16 k: line group p/2, k half p%2;  lane -> (t = 8*(p/2) + lane%8, k = 16*(p%2) + 4*(lane/8))
+//       one MMA (8 k) = 2 k chunks = 256 B further
+//   MN-major (m/n contiguous in global; lines = k), SWIZZLE_128B_BASE32B, atom = 4 k x 32 t (4 rows of 128 B,
+//       the 32-byte chunk index XORed with the row index: Swizzle<2,5,2> on the byte address):
+//       byte(t, k) = (t/32)*4096 + (k/4)*512 + (k%4)*128 + ((((t%32)/8) ^ (k%4)) * 32) + (t%8)*4
+//       LBO = 4096 (next 32 t), SBO = 512 (next 4 k); one MMA (8 k) = 2 atoms = 1024 B further
+//       patch p = 4 k x 32 t: k group p%8, t group p/8;  lane -> (k = 4*(p%8) + lane/8, t = 32*(p/8) + 4*(lane%8))
+template <bool KMAJOR>
+__device__ __forceinline__ float4 tc_patch_load(const Rows& R, int p, int lane, int t0, int dimT, int k0, int dimK) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (KMAJOR) {
+    const int t = t0 + 8 * (p >> 1) + (lane & 7);
+    const int k = k0 + 16 * (p & 1) + 4 * (lane >> 3);
+    if (t < dimT && k < dimK) v = __ldg(reinterpret_cast<const float4*>(row_ptr(R, t) + k));
+  } else {
+    const int k = k0 + 4 * (p & 7) + (lane >> 3);
+    const int t = t0 + 32 * (p >> 3) + 4 * (lane & 7);
+    if (k < dimK && t < dimT) v = __ldg(reinterpret_cast<const float4*>(row_ptr(R, k) + t));
+  }
+  return v;
+}
+template <bool KMAJOR>
+__device__ __forceinline__ uint32_t tc_patch_offset(int p, int lane) {
+  if (KMAJOR) return (uint32_t)((p >> 1) * 1024 + ((p & 1) * 4 + (lane >> 3)) * 128 + (lane & 7) * 16);
+  const int kr = lane >> 3, c16 = lane & 7;
+  return (uint32_t)((p >> 3) * 4096 + (p & 7) * 512 + kr * 128 + (((c16 >> 1) ^ kr) << 5) + (c16 & 1) * 16);
+}
+__device__ __forceinline__ void tc_split_store(char* hi, char* lo, uint32_t off, const float4& v) {
+  float4 h, l;
+  h.x = rna_tf32(v.x); h.y = rna_tf32(v.y); h.z = rna_tf32(v.z); h.w = rna_tf32(v.w);
+  l.x = rna_tf32(v.x - h.x); l.y = rna_tf32(v.y - h.y); l.z = rna_tf32(v.z - h.z); l.w = rna_tf32(v.w - h.w);
+  *reinterpret_cast<float4*>(hi + off) = h;
+  *reinterpret_cast<float4*>(lo + off) = l;
+}
+
+// EPI_* as in gemm.cuh. Output element (m, n) lives at C + n*ldc + m.
+struct TcParams {
+  int M, N, K;
+  int bn;  // N tile (multiple of 16, <= 256)
+  RowMap A, B;
+  float* cbase; long long c_gstride; const int* cidx; long long c_off; int ldc;
+  const float* bias_base; long long bias_gstride; const int* bias_idx; long long bias_off;  // bias[m] (EPI_FWD)
+  int act; float slope;
+  const float* saved; long long saved_gstride;  // EPI_BWD_DATA: saved[g] + n*ldc + m
+  float* adam_m; float* adam_v; const int* step; float lr, b1, b2, eps;  // EPI_ADAM
+};
+
+template <bool A_KMAJOR, bool B_KMAJOR, int EPI>
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_grouped_gemm_kernel(const TcParams p) {
+  extern __shared__ __align__(1024) char tc_smem[];
+  __shared__ __align__(8) unsigned long long bars[TC_STAGES + 1];
+  __shared__ uint32_t tmem_slot;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = blockIdx.z;
+  const int m0 = blockIdx.y * TC_BM;
+  const int n0 = blockIdx.x * p.bn;
+  const int bn = p.bn;
+
+  // stage layout: [A hi | A lo | B hi | B lo]
+  const uint32_t a_bytes = TC_BM * TC_BK * 4;
+  const int bn_pad = (bn + 31) & ~31;  // MN-major staging works in groups of 32 lines
+  const uint32_t b_bytes = (uint32_t)bn_pad * TC_BK * 4;
+  const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
+  // the swizzled layout XORs absolute address bits [7,9) into [5,7): every buffer starts 1024-aligned
+  char* smem = tc_smem + ((1024u - (smem_u32(tc_smem) & 1023u)) & 1023u);
+
+  // two accumulators of `acc_cols` columns: hi*hi in the first, the two correction products in the
+  // second. The tensor core truncates when it adds into an fp32 accumulator, so the error grows with
+  // the number of accumulations; keeping the 2^-11-sized corrections apart cuts that by three.
+  uint32_t acc_cols = 32;
+  while ((int)acc_cols < bn) acc_cols <<= 1;
+  const uint32_t ncols = 2 * acc_cols;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int i = 0; i <= TC_STAGES; ++i) mbar_init(smem_u32(&bars[i]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(smem_u32(&tmem_slot), ncols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = tmem_slot;
+
+  const Rows RA = resolve(p.A, g);
+  const Rows RB = resolve(p.B, g);
+  const int nkb = (p.K + TC_BK - 1) / TC_BK;
+  const int npb = B_KMAJOR ? (bn >> 2) : (bn_pad >> 2);  // patches of the B tile (128/4 = 32 for A)
+  const uint32_t idesc = umma_idesc_tf32(!A_KMAJOR, !B_KMAJOR, bn);
+
+  float4 ra[4], rb[8];
+  auto load_block = [&](int kb) {
+    const int k0 = kb * TC_BK;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) ra[i] = tc_patch_load<A_KMAJOR>(RA, warp + 8 * i, lane, m0, p.M, k0, p.K);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int pp = warp + 8 * i;
+      rb[i] = (pp < npb) ? tc_patch_load<B_KMAJOR>(RB, pp, lane, n0, p.N, k0, p.K) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+
+  load_block(0);
+  for (int kb = 0; kb < nkb; ++kb) {
+    const int s = kb % TC_STAGES;
+    const int use = kb / TC_STAGES;
+    if (use > 0) mbar_wait(smem_u32(&bars[s]), (uint32_t)((use - 1) & 1));  // MMAs that read stage s are done
+    char* st = smem + (size_t)s * stage_bytes;
+    char* a_hi = st;
+    char* a_lo = st + a_bytes;
+    char* b_hi = st + 2 * a_bytes;
+    char* b_lo = b_hi + b_bytes;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) tc_split_store(a_hi, a_lo, tc_patch_offset<A_KMAJOR>(warp + 8 * i, lane), ra[i]);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int pp = warp + 8 * i;
+      if (pp < npb) tc_split_store(b_hi, b_lo, tc_patch_offset<B_KMAJOR>(pp, lane), rb[i]);
+    }
+    fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core (async proxy)
+    if (kb + 1 < nkb) load_block(kb + 1);  // next block's loads fly across the barrier and the MMAs
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t sa_hi = smem_u32(a_hi), sa_lo = smem_u32(a_lo), sb_hi = smem_u32(b_hi), sb_lo = smem_u32(b_lo);
+      // K-major : LBO = 128 (next 16-byte k chunk), SBO = 1024 (next 8 lines), a k-step of 8 = 256 B
+      // MN-major: LBO = 4096 (next 32 lines), SBO = 512 (next 4 k), a k-step of 8 = 1024 B
+      const uint32_t a_lbo = A_KMAJOR ? 128u : 4096u, a_sbo = A_KMAJOR ? 1024u : 512u;
+      const uint32_t b_lbo = B_KMAJOR ? 128u : 4096u, b_sbo = B_KMAJOR ? 1024u : 512u;
+      const uint32_t a_step = A_KMAJOR ? 256u : 1024u, b_step = B_KMAJOR ? 256u : 1024u;
+      const uint32_t a_lay = A_KMAJOR ? UMMA_LAYOUT_NONE : UMMA_LAYOUT_SW128_BASE32B;
+      const uint32_t b_lay = B_KMAJOR ? UMMA_LAYOUT_NONE : UMMA_LAYOUT_SW128_BASE32B;
+#pragma unroll
+      for (int j = 0; j < TC_BK / 8; ++j) {
+        const uint64_t dah = umma_desc(sa_hi + j * a_step, a_lbo, a_sbo, a_lay);
+        const uint64_t dal = umma_desc(sa_lo + j * a_step, a_lbo, a_sbo, a_lay);
+        const uint64_t dbh = umma_desc(sb_hi + j * b_step, b_lbo, b_sbo, b_lay);
+        const uint64_t dbl = umma_desc(sb_lo + j * b_step, b_lbo, b_sbo, b_lay);
+        const uint32_t acc = (kb | j) ? 1u : 0u;
+        umma_tf32(tmem_d + acc_cols, dal, dbh, idesc, acc);
+        umma_tf32(tmem_d + acc_cols, dah, dbl, idesc, 1u);
+        umma_tf32(tmem_d, dah, dbh, idesc, acc);
+      }
+      umma_commit(smem_u32(&bars[s]));
+      if (kb + 1 == nkb) umma_commit(smem_u32(&bars[TC_STAGES]));
+    }
+  }
+
+  // ---- epilogue: TMEM -> registers -> fused op -> global ---------------------------------------
+  mbar_wait(smem_u32(&bars[TC_STAGES]), 0);
+  tc_fence_after();
+
+  const int q = warp & 3;        // TMEM lane quarter this warp may read
+  const int half = warp >> 2;    // warps w and w+4 share a quarter and alternate 16-column chunks
+  const int m = m0 + q * 32 + lane;
+  const bool m_ok = m < p.M;
+  const int rowid = p.cidx ? p.cidx[g] : g;
+  float* C = p.cbase + (long long)rowid * p.c_gstride + p.c_off;
+
+  float bias = 0.f;
+  if (EPI == EPI_FWD && p.bias_base && m_ok) {
+    const int brow = p.bias_idx ? p.bias_idx[g] : g;
+    bias = __ldg(p.bias_base + (long long)brow * p.bias_gstride + p.bias_off + m);
+  }
+  AdamScalars as = {};
+  float* Mo = nullptr;
+  float* Vo = nullptr;
+  if (EPI == EPI_ADAM) {
+    as = make_adam_scalars(p.step[rowid], p.lr, p.b1, p.b2, p.eps);
+    Mo = p.adam_m + (long long)rowid * p.c_gstride + p.c_off;
+    Vo = p.adam_v + (long long)rowid * p.c_gstride + p.c_off;
+  }
+  const float* S = (EPI == EPI_BWD_DATA && p.saved) ? p.saved + (long long)g * p.saved_gstride : nullptr;
+
+  for (int c = half; c < (bn >> 4); c += 2) {
+    float v[16], vc[16];
+    tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 16), v);
+    tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + acc_cols + (uint32_t)(c * 16), vc);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] += vc[j];
+    const int nb = n0 + c * 16;
+    if (!m_ok || nb >= p.N) continue;
+    if (EPI == EPI_ADAM) {
+      float w[16], mm[16], vv[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const long long off = (long long)(nb + j) * p.ldc + m;
+        const bool ok = nb + j < p.N;
+        w[j] = ok ? C[off] : 0.f;
+        mm[j] = ok ? Mo[off] : 0.f;
+        vv[j] = ok ? Vo[off] : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        if (nb + j < p.N) {
+          const long long off = (long long)(nb + j) * p.ldc + m;
+          adam_update(w[j], mm[j], vv[j], v[j], as);
+          C[off] = w[j]; Mo[off] = mm[j]; Vo[off] = vv[j];
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        if (nb + j < p.N) {
+          const long long off = (long long)(nb + j) * p.ldc + m;
+          float o = v[j];
+          if (EPI == EPI_FWD) o = act_fwd(o + bias, p.act, p.slope);
+          if (EPI == EPI_BWD_DATA && S) o *= act_bwd_from_out(__ldg(S + off), p.act, p.slope);
+          C[off] = o;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_d, ncols);
+}
+
+static inline int tc_pick_bn(int N) {
+  const int tiles = (N + TC_MAX_BN - 1) / TC_MAX_BN;
+  const int per = (N + tiles - 1) / tiles;
+  return (per + 15) / 16 * 16;
+}
+static inline size_t tc_smem_bytes(int bn) {
+  const size_t bn_pad = ((size_t)bn + 31) & ~(size_t)31;
+  return (size_t)TC_STAGES * (2 * TC_BM * TC_BK * 4 + 2 * bn_pad * TC_BK * 4) + 1024;
+}
+
+template <bool A_KMAJOR, bool B_KMAJOR, int EPI>
+static inline cudaError_t launch_tc_gemm(TcParams p, int G, cudaStream_t stream) {
+  if (G <= 0 || p.M <= 0 || p.N <= 0) return cudaSuccess;
+  p.bn = tc_pick_bn(p.N);
+  const size_t smem = tc_smem_bytes(p.bn);
+  static bool attr_set = false;  // per template instantiation
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(tc_grouped_gemm_kernel<A_KMAJOR, B_KMAJOR, EPI>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(TC_MAX_BN));
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  dim3 grid((p.N + p.bn - 1) / p.bn, (p.M + TC_BM - 1) / TC_BM, G);
+  tc_grouped_gemm_kernel<A_KMAJOR, B_KMAJOR, EPI><<<grid, TC_THREADS, smem, stream>>>(p);
+  return cudaGetLastError();
+}
+
+// The tensor-core path needs float4-addressable operands: 16-byte aligned bases / strides, the
+// contiguous extent a multiple of 4, and enough work per tile to be worth an MMA tile.
+static inline bool tc_rowmap_ok(const RowMap& m, int contiguous_extent) { return m.vec && (contiguous_extent % 4 == 0); }
+
+}  // namespace cgl

@@ -174,6 +174,17 @@ int cgl_mix_allreduce(cgl_comm_t comm, int C_local, int64_t n, const float* w_lo
                       const int32_t* rows, const float* src, int64_t ld_src, float* out,
                       cgl_stream_t stream);
 
+/* ---- kernel selection (tests / profiling) ------------------------------------------------------
+ * The Linear products run on one of two sm_100a kernels of this library, chosen by shape and alignment:
+ * the tcgen05/TMEM 3xTF32 grouped GEMM (wide, 16-byte aligned layers) or the exact-fp32 FFMA grouped GEMM
+ * (narrow or unaligned layers). mode: 0 = automatic (default), 1 = FFMA only, 2 = tcgen05 wherever the
+ * operands are addressable by it. Process-wide; not a reference knob.                                */
+#define CGL_GEMM_AUTO 0
+#define CGL_GEMM_FFMA 1
+#define CGL_GEMM_TC 2
+int cgl_set_gemm_mode(int mode);
+int cgl_get_gemm_mode(void);
+
 /* ---- building blocks (exported for tests and for the host-side generator step) -------------
  * Grouped Linear over G independent groups, fp32:
  *   fwd : y[g] = act(x[g] W[g]^T + b[g])        x [rows,in] (ldx), W [out,in], y [rows,out]

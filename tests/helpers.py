@@ -78,14 +78,15 @@ def assert_params_close(a, b, lr=2e-4, steps=1, tag="", strict=True):
         assert no <= max(2, 1e-3 * a.numel()), (tag, "elements outside 1e-5", no, a.numel())
 
 
-def assert_rows_close(a, b, tag="", row_frac=0.97):
+def assert_rows_close(a, b, tag="", row_frac=0.97, tol=1e-5):
     """Activation-gradient tensors [rows, width] (dLoss/dXg): >= 97 % of the rows within 1e-5 of the
-    tensor's scale; a row may differ where a LeakyReLU pre-activation of that sample sits on the kink."""
+    tensor's scale; a row may differ where a LeakyReLU pre-activation of that sample sits on the kink
+    (one flipped unit of the 256-wide layer moves that sample's row by ~8 %, i.e. ~1 % of the batch's L2)."""
     a, b = a.detach().double().cpu(), b.detach().double().cpu()
     a, b = a.reshape(-1, a.shape[-1]), b.reshape(-1, b.shape[-1])
     row_err = (a - b).abs().max(dim=1).values / b.abs().max().clamp_min(1e-30)
-    ok = (row_err <= 1e-5).double().mean().item()
-    assert ok >= row_frac, (tag, "rows within 1e-5", ok)
+    ok = (row_err <= tol).double().mean().item()
+    assert ok >= row_frac, (tag, "rows within tol", tol, ok)
     assert rel_l2(a, b) < 5e-2, (tag, "rel_l2", rel_l2(a, b))
 
 

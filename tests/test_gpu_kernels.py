@@ -56,8 +56,9 @@ def test_d_step_and_g_loss_match_oracle(lib, arch, scale, steps):
             l_ref.backward()
             assert abs(d_gpu[g].item() - d_ref.item()) < LOSS_TOL, (it, g, d_gpu[g].item(), d_ref.item())
             assert abs(l_gpu[g].item() - l_ref.item()) < LOSS_TOL, (it, g)
-            # after an Adam step the two D's differ at the ill-conditioned elements (see assert_params_close)
-            assert rel_l2(xg_dev.grad[g], x.grad) < 1e-3, (it, g, rel_l2(xg_dev.grad[g], x.grad))
+            # after an Adam step the two D's differ at the ill-conditioned elements (see assert_params_close),
+            # and a sample whose pre-activation sits on the LeakyReLU kink flips a whole row of dLoss/dXg
+            assert_rows_close(xg_dev.grad[g], x.grad, tag=(it, g), row_frac=0.9, tol=1e-4)
     for g in range(G):
         # layer-wise (a small layer must not hide behind a large one)
         off = 0
