@@ -234,6 +234,8 @@ def run_b200(args):
         torch.cuda.current_stream().synchronize()     # the user reads the round's losses
         return (nxt, ev2)
 
+    launch0 = [0]
+
     def timed(fn, steps, warmup, e2e=False):
         pending = None
         if e2e:
@@ -244,8 +246,7 @@ def run_b200(args):
         for i in range(warmup):
             pending = fn(i, pending) if e2e else fn(i)
         sync_all()
-        sim.bank.launches = 0
-        sim.G.launches = 0
+        launch0[0] = abi.launch_count()
         start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         start.record()
         for i in range(steps):
@@ -262,7 +263,7 @@ def run_b200(args):
         sampler.start()
     sim.profile = True
     ms = timed(resident_round, args.steps, args.warmup)
-    launches = sim.bank.launches + sim.G.launches
+    launches = abi.launch_count() - launch0[0]
     client_ms = sim.client_step_ms()
     sim.profile = False
     clocks = sampler.stop() if rank == 0 else None

@@ -49,6 +49,7 @@ _i32, _i64, _f32, _sz = C.c_int, C.c_int64, C.c_float, C.c_size_t
 lib.cgl_version.restype = C.c_char_p
 lib.cgl_last_error.restype = C.c_char_p
 lib.cgl_device_ok.restype = C.c_int
+lib.cgl_launch_count.restype = C.c_longlong
 lib.cgl_arch_describe.argtypes = [_i32, C.POINTER(MlpDesc)]
 lib.cgl_mlp_layout_of.argtypes = [C.POINTER(MlpDesc), C.POINTER(MlpLayout)]
 lib.cgl_d_step_workspace_bytes.argtypes = [C.POINTER(MlpDesc), _i32, _i32]
@@ -68,6 +69,11 @@ lib.cgl_comm_init.argtypes = [_i32, _i32, _p, C.POINTER(_p)]
 lib.cgl_comm_destroy.argtypes = [_p]
 lib.cgl_allreduce_sum.argtypes = [_p, _p, _i64, _p]
 lib.cgl_mix_allreduce.argtypes = [_p, _i32, _i64, _p, _p, _p, _i64, _p, _p]
+lib.cgl_mlp_workspace_bytes.argtypes = [C.POINTER(MlpDesc), _i32, _i32]
+lib.cgl_mlp_workspace_bytes.restype = _sz
+lib.cgl_mlp_forward.argtypes = [C.POINTER(MlpDesc), _i32, _p, _i64, _p, _p, _i64, _i32, _p, _i64, _p, _i32, _p, _p, _sz, _p]
+lib.cgl_mlp_backward.argtypes = [C.POINTER(MlpDesc), _i32, _p, _p, _p, _i64, _p, _p, C.POINTER(TrainCfg), _p, _i64, _p,
+                                 _i32, _p, _p, _p, _p, _sz, _p]
 lib.cgl_set_gemm_mode.argtypes = [_i32]
 lib.cgl_get_gemm_mode.restype = C.c_int
 lib.cgl_linear_fwd.argtypes = [_i32, _i32, _i32, _i32, _p, _i64, _p, _i64, _p, _i64, _i64, _i32, _f32, _p, _i64, _p]
@@ -78,7 +84,7 @@ lib.cgl_linear_wgrad.argtypes = [_i32, _i32, _i32, _i32, _p, _i64, _p, _i64, _p,
 for _name in ("cgl_arch_describe", "cgl_mlp_layout_of", "cgl_d_step", "cgl_g_loss", "cgl_dxg_reduce",
               "cgl_adam_rows", "cgl_mix_csr", "cgl_wsum", "cgl_bcast_mix", "cgl_comm_unique_id",
               "cgl_comm_init", "cgl_comm_destroy", "cgl_allreduce_sum", "cgl_mix_allreduce",
-              "cgl_linear_fwd", "cgl_linear_bwd_data", "cgl_linear_wgrad", "cgl_set_gemm_mode"):
+              "cgl_linear_fwd", "cgl_linear_bwd_data", "cgl_linear_wgrad", "cgl_set_gemm_mode", "cgl_mlp_forward", "cgl_mlp_backward"):
     getattr(lib, _name).restype = C.c_int
 
 
@@ -89,6 +95,10 @@ def check(rc):
 
 def version():
     return lib.cgl_version().decode()
+
+
+def launch_count():
+    return int(lib.cgl_launch_count())
 
 
 def device_ok():

@@ -12,9 +12,13 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+static long long g_launches = 0;
+void count_launch(int n) { g_launches += n; }
 }  // namespace cgl
 
 using namespace cgl;
+
+extern "C" long long cgl_launch_count(void) { return g_launches; }
 
 extern "C" const char* cgl_version(void) { return "cgl_b200 0.1.0 (sm_100a)"; }
 extern "C" const char* cgl_last_error(void) { return g_err; }

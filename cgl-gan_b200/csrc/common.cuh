@@ -11,6 +11,8 @@ namespace cgl {
 
 // ---- error reporting (thread-local message, C return codes) -------------------------------
 void set_error(const char* fmt, ...);
+// every kernel launch of the library is counted (cgl_launch_count: bench.py's gpu_launches)
+void count_launch(int n = 1);
 
 #define CGL_CHECK_CUDA(expr)                                                          \
   do {                                                                                \
@@ -21,7 +23,11 @@ void set_error(const char* fmt, ...);
     }                                                                                 \
   } while (0)
 
-#define CGL_CHECK_LAUNCH() CGL_CHECK_CUDA(cudaGetLastError())
+#define CGL_CHECK_LAUNCH()               \
+  do {                                   \
+    cgl::count_launch();                 \
+    CGL_CHECK_CUDA(cudaGetLastError());  \
+  } while (0)
 
 #define CGL_REQUIRE(cond, ...)      \
   do {                              \

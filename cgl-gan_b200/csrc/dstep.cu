@@ -1,10 +1,17 @@
 // dstep.cu -- the per-client discriminator step and generator-loss evaluation (K1/K2).
 // Reference: Worker.train, CGLGAN/2DMG/main.py:344-375; capgan.py:316-349; MDGAN/MNIST/mdgan.py:266-297.
 #include "linear.cuh"
+#include <stdlib.h>
 
 namespace cgl {
 
-static int g_gemm_mode = GEMM_AUTO;
+// CGL_GEMM_MODE=0|1|2 in the environment presets cgl_set_gemm_mode (profiling and bisecting only)
+static int initial_gemm_mode() {
+  const char* e = getenv("CGL_GEMM_MODE");
+  if (e && e[0] >= '0' && e[0] <= '2' && e[1] == 0) return e[0] - '0';
+  return GEMM_AUTO;
+}
+static int g_gemm_mode = initial_gemm_mode();
 int gemm_mode() { return g_gemm_mode; }
 
 // ---------------------------------------------------------------------------------------------

@@ -369,6 +369,7 @@ static inline cudaError_t launch_grouped_gemm(const GemmParams& p, int G, cudaSt
   if (G <= 0 || p.M <= 0 || p.N <= 0) return cudaSuccess;
   dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, G);
   grouped_gemm_kernel<A_KMAJOR, B_KMAJOR, EPI><<<grid, GEMM_THREADS, 0, stream>>>(p);
+  count_launch();
   return cudaGetLastError();
 }
 

@@ -1,0 +1,324 @@
+// gstep.cu -- the generator side of a round (row a4 / a5 of SURVEY.md section 8): forward of a stack of
+// Linear [+ BatchNorm1d(eps = 0.8, batch statistics)] + LeakyReLU / Tanh over G independent groups
+// (edge servers, heads, or FL clients), and its backward with the Adam step fused in.
+// Reference: Server.train, CGLGAN/2DMG/main.py:229-234,254-276; mixed-gan.py:238-292;
+//            model/mnist_model.py:5-29 (Generator), :32-66 (MixGenerator); FL: FLGAN/MNIST/flgan.py:251-269.
+#include "linear.cuh"
+
+namespace cgl {
+
+// ---------------------------------------------------------------------------------------------
+// BatchNorm1d, training mode, one thread per (group, feature); rows are walked three times (the
+// [rows x 128] slab of a CTA stays in L1). torch semantics: biased variance for the normalisation,
+// unbiased for running_var, momentum 0.1 (model/mnist_model.py:13 passes eps = 0.8 positionally).
+//   u [G][rows][F] -> h = act((u - mean) * invstd * gamma + beta);  saves mean / invstd per (g, f)
+// ---------------------------------------------------------------------------------------------
+struct BnFwdParams {
+  int rows, F;
+  const float* u; long long u_gstride;
+  float* h; long long h_gstride;
+  const float* params; long long ldp; const int* ids; long long gamma_off, beta_off;
+  float* stats; long long ld_stats; long long mean_off, var_off;  // running stats row (NULL: none)
+  float* save_mean; float* save_invstd;                            // [G][F]
+  float eps, momentum; int train; int act; float slope;
+};
+
+__global__ void __launch_bounds__(128) bn_fwd_kernel(const BnFwdParams p) {
+  const int g = blockIdx.y;
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= p.F) return;
+  const int rowid = p.ids ? p.ids[g] : g;
+  const float* u = p.u + (long long)g * p.u_gstride + f;
+  float* h = p.h + (long long)g * p.h_gstride + f;
+  const float gamma = __ldg(p.params + (long long)rowid * p.ldp + p.gamma_off + f);
+  const float beta = __ldg(p.params + (long long)rowid * p.ldp + p.beta_off + f);
+  float mean, var;
+  const int n = p.rows;
+  if (p.train) {
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int r = 0;
+    for (; r + 3 < n; r += 4) {
+      s0 += u[(long long)r * p.F]; s1 += u[(long long)(r + 1) * p.F];
+      s2 += u[(long long)(r + 2) * p.F]; s3 += u[(long long)(r + 3) * p.F];
+    }
+    for (; r < n; ++r) s0 += u[(long long)r * p.F];
+    mean = ((s0 + s1) + (s2 + s3)) / (float)n;
+    s0 = s1 = s2 = s3 = 0.f;
+    r = 0;
+    for (; r + 3 < n; r += 4) {
+      float d0 = u[(long long)r * p.F] - mean, d1 = u[(long long)(r + 1) * p.F] - mean;
+      float d2 = u[(long long)(r + 2) * p.F] - mean, d3 = u[(long long)(r + 3) * p.F] - mean;
+      s0 = fmaf(d0, d0, s0); s1 = fmaf(d1, d1, s1); s2 = fmaf(d2, d2, s2); s3 = fmaf(d3, d3, s3);
+    }
+    for (; r < n; ++r) { float d0 = u[(long long)r * p.F] - mean; s0 = fmaf(d0, d0, s0); }
+    const float ss = (s0 + s1) + (s2 + s3);
+    var = ss / (float)n;
+    if (p.stats) {
+      float* rm = p.stats + (long long)rowid * p.ld_stats + p.mean_off + f;
+      float* rv = p.stats + (long long)rowid * p.ld_stats + p.var_off + f;
+      const float unbiased = n > 1 ? ss / (float)(n - 1) : var;
+      *rm = (1.f - p.momentum) * *rm + p.momentum * mean;
+      *rv = (1.f - p.momentum) * *rv + p.momentum * unbiased;
+    }
+  } else {
+    mean = p.stats[(long long)rowid * p.ld_stats + p.mean_off + f];
+    var = p.stats[(long long)rowid * p.ld_stats + p.var_off + f];
+  }
+  const float invstd = 1.f / sqrtf(var + p.eps);
+  if (p.save_mean) {
+    p.save_mean[(long long)g * p.F + f] = mean;
+    p.save_invstd[(long long)g * p.F + f] = invstd;
+  }
+  const float a = invstd * gamma;
+  for (int r = 0; r < n; ++r) {
+    const float y = (u[(long long)r * p.F] - mean) * a + beta;
+    h[(long long)r * p.F] = act_fwd(y, p.act, p.slope);
+  }
+}
+
+// Backward of the same: dz is the gradient wrt the BatchNorm OUTPUT (activation derivative already
+// applied); overwritten in place with the gradient wrt the BatchNorm input u. gamma / beta take
+// their Adam step here (torch.optim.Adam on bn.weight / bn.bias).
+struct BnBwdParams {
+  int rows, F;
+  float* dz; long long dz_gstride;
+  const float* u; long long u_gstride;
+  const float* save_mean; const float* save_invstd;
+  float* params; float* adam_m; float* adam_v; long long ldp; const int* ids; long long gamma_off, beta_off;
+  const int* step; float lr, b1, b2, eps;
+};
+
+__global__ void __launch_bounds__(128) bn_bwd_kernel(const BnBwdParams p) {
+  const int g = blockIdx.y;
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= p.F) return;
+  const int rowid = p.ids ? p.ids[g] : g;
+  float* dz = p.dz + (long long)g * p.dz_gstride + f;
+  const float* u = p.u + (long long)g * p.u_gstride + f;
+  const float mean = p.save_mean[(long long)g * p.F + f];
+  const float invstd = p.save_invstd[(long long)g * p.F + f];
+  const int n = p.rows;
+  float sb0 = 0.f, sb1 = 0.f, sg0 = 0.f, sg1 = 0.f;
+  int r = 0;
+  for (; r + 1 < n; r += 2) {
+    const float d0 = dz[(long long)r * p.F], d1 = dz[(long long)(r + 1) * p.F];
+    sb0 += d0; sb1 += d1;
+    sg0 = fmaf(d0, u[(long long)r * p.F] - mean, sg0);
+    sg1 = fmaf(d1, u[(long long)(r + 1) * p.F] - mean, sg1);
+  }
+  for (; r < n; ++r) {
+    const float d0 = dz[(long long)r * p.F];
+    sb0 += d0;
+    sg0 = fmaf(d0, u[(long long)r * p.F] - mean, sg0);
+  }
+  const float dbeta = sb0 + sb1;
+  const float dotp = sg0 + sg1;          // sum dz * (u - mean)
+  const float dgamma = dotp * invstd;
+  const long long go = (long long)rowid * p.ldp + p.gamma_off + f;
+  const long long bo = (long long)rowid * p.ldp + p.beta_off + f;
+  const float gamma = p.params[go];
+  // du = (dz - dbeta/n - (u - mean) * invstd^2 * dotp / n) * invstd * gamma     (ATen batch_norm_backward)
+  const float k = dotp * invstd * invstd / (float)n;
+  const float mb = dbeta / (float)n;
+  const float a = invstd * gamma;
+  for (r = 0; r < n; ++r) {
+    const float d = dz[(long long)r * p.F];
+    dz[(long long)r * p.F] = (d - mb - (u[(long long)r * p.F] - mean) * k) * a;
+  }
+  const AdamScalars s = make_adam_scalars(p.step[rowid], p.lr, p.b1, p.b2, p.eps);
+  {
+    float w = gamma, mm = p.adam_m[go], vv = p.adam_v[go];
+    adam_update(w, mm, vv, dgamma, s);
+    p.params[go] = w; p.adam_m[go] = mm; p.adam_v[go] = vv;
+  }
+  {
+    float w = p.params[bo], mm = p.adam_m[bo], vv = p.adam_v[bo];
+    adam_update(w, mm, vv, dbeta, s);
+    p.params[bo] = w; p.adam_m[bo] = mm; p.adam_v[bo] = vv;
+  }
+}
+
+// dz = dy * act'(y), y the saved activation output (the Tanh of the generator's last layer)
+__global__ void act_bwd_kernel(long long n, const float* __restrict__ dy, const float* __restrict__ y, float* dz,
+                               int act, float slope) {
+  long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    const float4 a = *reinterpret_cast<const float4*>(dy + i);
+    const float4 b = *reinterpret_cast<const float4*>(y + i);
+    float4 o;
+    o.x = a.x * act_bwd_from_out(b.x, act, slope); o.y = a.y * act_bwd_from_out(b.y, act, slope);
+    o.z = a.z * act_bwd_from_out(b.z, act, slope); o.w = a.w * act_bwd_from_out(b.w, act, slope);
+    *reinterpret_cast<float4*>(dz + i) = o;
+  } else {
+    for (; i < n; ++i) dz[i] = dy[i] * act_bwd_from_out(y[i], act, slope);
+  }
+}
+
+__global__ void bump_rows_step_kernel(int G, int* step, const int* ids) {
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < G) step[ids ? ids[g] : g] += 1;
+}
+
+// ---- workspace ----------------------------------------------------------------------------------
+static inline size_t up256(size_t x) { return (x + 255) / 256 * 256; }
+
+struct MlpWs {
+  float* H[CGL_MAX_LAYERS + 1];   // H[l], l = 1..L-1: input of layer l (post-activation output of layer l-1)
+  float* U[CGL_MAX_LAYERS];       // pre-BatchNorm linear output of layer l (bn[l] only)
+  float* mean[CGL_MAX_LAYERS];
+  float* invstd[CGL_MAX_LAYERS];
+  float* dZ[2];                   // backward ping-pong, G*rows*maxdim each
+  size_t bytes;
+};
+static MlpWs mlp_carve(const cgl_mlp_desc* a, int G, int rows, void* base) {
+  MlpWs w = {};
+  char* p = (char*)base;
+  size_t off = 0;
+  int maxdim = 0;
+  for (int l = 0; l <= a->n_layers; ++l) maxdim = a->dims[l] > maxdim ? a->dims[l] : maxdim;
+  for (int l = 0; l < a->n_layers; ++l) {
+    if (l > 0) { w.H[l] = (float*)(p + off); off += up256((size_t)G * rows * a->dims[l] * 4); }
+    if (a->bn[l]) {
+      w.U[l] = (float*)(p + off); off += up256((size_t)G * rows * a->dims[l + 1] * 4);
+      w.mean[l] = (float*)(p + off); off += up256((size_t)G * a->dims[l + 1] * 4);
+      w.invstd[l] = (float*)(p + off); off += up256((size_t)G * a->dims[l + 1] * 4);
+    }
+  }
+  for (int i = 0; i < 2; ++i) { w.dZ[i] = (float*)(p + off); off += up256((size_t)G * rows * maxdim * 4); }
+  w.bytes = off + 256;
+  return w;
+}
+
+static int validate_mlp(const cgl_mlp_desc* a) {
+  CGL_REQUIRE(a != nullptr, "arch is NULL");
+  CGL_REQUIRE(a->n_layers >= 1 && a->n_layers <= CGL_MAX_LAYERS, "n_layers=%d out of range", a->n_layers);
+  for (int i = 0; i < a->n_layers; ++i) CGL_REQUIRE(a->dims[i] > 0 && a->dims[i + 1] > 0, "bad width at layer %d", i);
+  return CGL_OK;
+}
+
+}  // namespace cgl
+
+using namespace cgl;
+
+extern "C" size_t cgl_mlp_workspace_bytes(const cgl_mlp_desc* arch, int G, int rows) {
+  if (!arch || G <= 0 || rows <= 0 || arch->n_layers < 1 || arch->n_layers > CGL_MAX_LAYERS) return 0;
+  return mlp_carve(arch, G, rows, nullptr).bytes;
+}
+
+extern "C" int cgl_mlp_forward(const cgl_mlp_desc* arch, int G, const float* params, int64_t ldp, const int32_t* ids,
+                               float* bn_stats, int64_t ld_stats, int train, const float* x, int64_t x_gstride,
+                               const int32_t* x_idx, int rows, float* y, void* workspace, size_t workspace_bytes,
+                               cgl_stream_t stream) {
+  int rc = validate_mlp(arch);
+  if (rc) return rc;
+  if (G == 0) return CGL_OK;
+  CGL_REQUIRE(G > 0 && G <= 65535, "G=%d out of range (1..65535 groups per call)", G);
+  CGL_REQUIRE(rows > 0, "rows must be positive");
+  CGL_REQUIRE(params && x && y && workspace, "NULL tensor pointer");
+  cgl_mlp_layout lay;
+  rc = cgl_mlp_layout_of(arch, &lay);
+  if (rc) return rc;
+  CGL_REQUIRE(ldp >= lay.n_params, "ldp=%lld smaller than packed row (%lld)", (long long)ldp, (long long)lay.n_params);
+  CGL_REQUIRE(lay.n_bn_stats == 0 || (bn_stats && ld_stats >= lay.n_bn_stats), "BatchNorm layers need a running-stats buffer");
+  MlpWs w = mlp_carve(arch, G, rows, workspace);
+  if (workspace_bytes < w.bytes) {
+    set_error("workspace too small: %zu < %zu", workspace_bytes, w.bytes);
+    return CGL_EWORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int L = arch->n_layers;
+  for (int l = 0; l < L; ++l) {
+    const int in = arch->dims[l], out = arch->dims[l + 1];
+    RowMap X = (l == 0) ? single_rows(x, x_gstride, x_idx, in) : single_rows(w.H[l], (long long)rows * in, nullptr, in);
+    float* dst = (l + 1 < L) ? w.H[l + 1] : y;
+    if (!arch->bn[l]) {
+      CGL_CHECK_CUDA(run_linear_fwd(G, rows, in, out, X, params, ldp, ids, lay.w_off[l], lay.b_off[l], arch->act[l],
+                                    arch->lrelu_slope, dst, (long long)rows * out, st));
+    } else {
+      CGL_CHECK_CUDA(run_linear_fwd(G, rows, in, out, X, params, ldp, ids, lay.w_off[l], lay.b_off[l], CGL_ACT_NONE,
+                                    0.f, w.U[l], (long long)rows * out, st));
+      BnFwdParams b = {};
+      b.rows = rows; b.F = out;
+      b.u = w.U[l]; b.u_gstride = (long long)rows * out;
+      b.h = dst; b.h_gstride = (long long)rows * out;
+      b.params = params; b.ldp = ldp; b.ids = ids; b.gamma_off = lay.bn_w_off[l]; b.beta_off = lay.bn_b_off[l];
+      b.stats = bn_stats; b.ld_stats = ld_stats; b.mean_off = lay.bn_mean_off[l]; b.var_off = lay.bn_var_off[l];
+      b.save_mean = w.mean[l]; b.save_invstd = w.invstd[l];
+      b.eps = arch->bn_eps; b.momentum = arch->bn_momentum; b.train = train;
+      b.act = arch->act[l]; b.slope = arch->lrelu_slope;
+      dim3 grid((out + 127) / 128, G);
+      bn_fwd_kernel<<<grid, 128, 0, st>>>(b);
+      CGL_CHECK_LAUNCH();
+    }
+  }
+  return CGL_OK;
+}
+
+extern "C" int cgl_mlp_backward(const cgl_mlp_desc* arch, int G, float* params, float* adam_m, float* adam_v,
+                                int64_t ldp, int32_t* step, const int32_t* ids, const cgl_train_cfg* cfg,
+                                const float* x, int64_t x_gstride, const int32_t* x_idx, int rows, const float* y,
+                                const float* dy, float* dx, void* workspace, size_t workspace_bytes,
+                                cgl_stream_t stream) {
+  int rc = validate_mlp(arch);
+  if (rc) return rc;
+  if (G == 0) return CGL_OK;
+  CGL_REQUIRE(cfg != nullptr, "cfg is NULL");
+  CGL_REQUIRE(G > 0 && G <= 65535, "G=%d out of range (1..65535 groups per call)", G);
+  CGL_REQUIRE(rows > 0, "rows must be positive");
+  CGL_REQUIRE(params && adam_m && adam_v && step && x && y && dy && workspace, "NULL tensor pointer");
+  cgl_mlp_layout lay;
+  rc = cgl_mlp_layout_of(arch, &lay);
+  if (rc) return rc;
+  CGL_REQUIRE(ldp >= lay.n_params, "ldp smaller than packed row");
+  MlpWs w = mlp_carve(arch, G, rows, workspace);
+  if (workspace_bytes < w.bytes) {
+    set_error("workspace too small: %zu < %zu", workspace_bytes, w.bytes);
+    return CGL_EWORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int L = arch->n_layers;
+  bump_rows_step_kernel<<<(G + 127) / 128, 128, 0, st>>>(G, step, ids);
+  CGL_CHECK_LAUNCH();
+
+  // gradient wrt the last layer's pre-activation
+  int cur = 0;
+  {
+    const long long n = (long long)G * rows * arch->dims[L];
+    const long long nthreads = (n + 3) / 4;
+    act_bwd_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, st>>>(n, dy, y, w.dZ[cur], arch->act[L - 1],
+                                                                       arch->lrelu_slope);
+    CGL_CHECK_LAUNCH();
+  }
+  const AdamArgs ad = {adam_m, adam_v, step, cfg->lr, cfg->beta1, cfg->beta2, cfg->eps};
+  for (int l = L - 1; l >= 0; --l) {
+    const int in = arch->dims[l], out = arch->dims[l + 1];
+    float* dU = w.dZ[cur];
+    if (arch->bn[l]) {
+      BnBwdParams b = {};
+      b.rows = rows; b.F = out;
+      b.dz = dU; b.dz_gstride = (long long)rows * out;
+      b.u = w.U[l]; b.u_gstride = (long long)rows * out;
+      b.save_mean = w.mean[l]; b.save_invstd = w.invstd[l];
+      b.params = params; b.adam_m = adam_m; b.adam_v = adam_v; b.ldp = ldp; b.ids = ids;
+      b.gamma_off = lay.bn_w_off[l]; b.beta_off = lay.bn_b_off[l];
+      b.step = step; b.lr = cfg->lr; b.b1 = cfg->beta1; b.b2 = cfg->beta2; b.eps = cfg->eps;
+      dim3 grid((out + 127) / 128, G);
+      bn_bwd_kernel<<<grid, 128, 0, st>>>(b);
+      CGL_CHECK_LAUNCH();
+    }
+    // data gradient first: it reads W_l, which the weight-gradient kernel below overwrites (fused Adam)
+    if (l > 0) {
+      CGL_CHECK_CUDA(run_linear_bwd_data(G, rows, in, out, dU, (long long)rows * out, params, ldp, ids, lay.w_off[l],
+                                         w.H[l], (long long)rows * in, arch->act[l - 1], arch->lrelu_slope,
+                                         w.dZ[cur ^ 1], (long long)rows * in, st));
+    } else if (dx) {
+      CGL_CHECK_CUDA(run_linear_bwd_data(G, rows, in, out, dU, (long long)rows * out, params, ldp, ids, lay.w_off[0],
+                                         nullptr, 0, CGL_ACT_NONE, 0.f, dx, (long long)rows * in, st));
+    }
+    RowMap Xin = (l == 0) ? single_rows(x, x_gstride, x_idx, in) : single_rows(w.H[l], (long long)rows * in, nullptr, in);
+    CGL_CHECK_CUDA(run_linear_wgrad(G, rows, in, out, dU, (long long)rows * out, Xin, params, ldp, ids, lay.w_off[l],
+                                    lay.b_off[l], &ad, st));
+    cur ^= 1;
+  }
+  return CGL_OK;
+}

@@ -131,6 +131,7 @@ static inline cudaError_t run_linear_wgrad(int G, int rows, int in, int out, con
       bias_grad_kernel<false><<<grid, 128, 0, st>>>(rows, out, dy, dy_gstride, base, ld, ids, b_off, nullptr, nullptr,
                                                     nullptr, 0.f, 0.f, 0.f, 0.f);
     }
+    count_launch();
     return cudaGetLastError();
   }
   GemmParams p = wgrad_params(rows, in, out, dy, dy_gstride, X, base, ld, ids, w_off, b_off);

@@ -12,18 +12,21 @@
 // widths 784/512/256/1024 fill it, while N takes any multiple of 16 up to 256 (200 -> 208, 100 -> 112).
 //
 // Precision: the reference is strict fp32 (torch default, allow_tf32 = False). Each fp32 operand x is
-// split in registers into hi = rna_tf32(x), lo = rna_tf32(x - hi); three MMAs accumulate
-// lo*hi + hi*lo + hi*hi in the fp32 TMEM accumulator (the dropped lo*lo term is ~2^-22 relative).
+// split in registers into hi = rna_tf32(x), lo = rna_tf32(x - hi); three MMAs per k-step accumulate
+// lo*hi + hi*lo (correction region) and hi*hi (rotating main regions) in fp32 TMEM accumulators that the
+// epilogue adds up (the dropped lo*lo term is ~2^-22 relative; see "TMEM plan" below for the regions).
 // Because the split needs a register pass anyway, operands are staged global -> registers -> shared
 // (whole 64/128-byte row segments, written straight into the canonical UMMA shared-memory layouts,
 // conflict-free) instead of by TMA; ragged / concatenated / index-selected row sources
 // (RowMap) come for free.
 //
-// Pipeline per CTA (256 threads, 128 x BN output tile, BK = 32):
-//   all threads: LDG next k-block -> registers | split -> STS stage s | fence.proxy.async | barrier
-//   thread 0   : 12 tcgen05.mma (4 k-steps x 3 split products) on stage s, tcgen05.commit -> empty[s]
-//   two stages; the commit mbarrier releases a stage for overwriting. Epilogue: tcgen05.ld 32x32b.x16,
-//   fused bias+activation / activation derivative / Adam, coalesced stores.
+// Pipeline per CTA (128 x BN output tile, BK = 32, 2..4 shared-memory stages, no CTA-wide barrier in the loop):
+//   warps 0..7 : LDG (two k-blocks in flight per thread) -> split -> STS stage s -> fence.proxy.async
+//                -> mbarrier arrive full[s]; wait empty[s] before a stage is overwritten
+//   warp 8     : one thread waits full[s], issues 12 tcgen05.mma (4 k-steps x 3 split products),
+//                tcgen05.commit -> empty[s]; a last commit -> done
+//   epilogue   : warps 0..7 wait done, tcgen05.ld 32x32b.x16 of every region, fused bias+activation /
+//                activation derivative / Adam, coalesced stores.
 #pragma once
 #include "gemm.cuh"
 
@@ -31,8 +34,10 @@ namespace cgl {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 32;
-constexpr int TC_STAGES = 2;
-constexpr int TC_THREADS = 256;
+constexpr int TC_MAX_STAGES = 4;
+constexpr int TC_LOADER_THREADS = 256;  // warps 0..7: operand staging, then the epilogue
+constexpr int TC_MMA_WARP = 8;          // warp 8: TMEM allocation and the single MMA-issuing thread
+constexpr int TC_THREADS = TC_LOADER_THREADS + 32;
 constexpr int TC_MAX_BN = 256;
 
 // ---- PTX wrappers ----------------------------------------------------------------------------
@@ -40,6 +45,9 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok = 0;
@@ -162,7 +170,8 @@ __device__ __forceinline__ void tc_split_store(char* hi, char* lo, uint32_t off,
 // EPI_* as in gemm.cuh. Output element (m, n) lives at C + n*ldc + m.
 struct TcParams {
   int M, N, K;
-  int bn;  // N tile (multiple of 16, <= 256)
+  int bn;        // N tile (multiple of 16, <= 256)
+  int n_stages;  // shared-memory stages (2..TC_MAX_STAGES)
   RowMap A, B;
   float* cbase; long long c_gstride; const int* cidx; long long c_off; int ldc;
   const float* bias_base; long long bias_gstride; const int* bias_idx; long long bias_off;  // bias[m] (EPI_FWD)
@@ -171,10 +180,30 @@ struct TcParams {
   float* adam_m; float* adam_v; const int* step; float lr, b1, b2, eps;  // EPI_ADAM
 };
 
-template <bool A_KMAJOR, bool B_KMAJOR, int EPI>
+// TMEM plan (512 columns, 1 CTA per SM). The tensor core TRUNCATES when it adds into an fp32
+// accumulator, a one-sided error that grows with the number of accumulations and that the reductions
+// downstream (BatchNorm, weight gradients, the client sum) do not average away. So the accumulator is
+// split into regions of `stride` = round_up(bn, 32) columns:
+//   region 0            : the two correction products (lo*hi + hi*lo), 2^-11 of the result
+//   regions 1..n_main   : hi*hi, k-step ks goes to region 1 + ks % n_main
+// and the epilogue adds the regions in fp32 with round-to-nearest. The host picks bn so that no region
+// takes more than TC_MAX_ACCUM accumulations (tc_pick_bn).
+constexpr int TC_MAX_ACCUM = 36;
+constexpr int TC_TMEM_COLS = 512;
+constexpr int TC_MAX_MAIN = 7;
+__host__ __device__ inline int tc_region_stride(int bn) { return (bn + 31) & ~31; }
+__host__ __device__ inline int tc_n_main(int bn) {
+  int r = TC_TMEM_COLS / tc_region_stride(bn) - 1;
+  return r > TC_MAX_MAIN ? TC_MAX_MAIN : r;
+}
+
+// NB = B patches per loader warp (4: bn <= 128, 8: bn <= 256); 8 loader warps + 1 MMA warp.
+template <bool A_KMAJOR, bool B_KMAJOR, int EPI, int NB>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_grouped_gemm_kernel(const TcParams p) {
   extern __shared__ __align__(1024) char tc_smem[];
-  __shared__ __align__(8) unsigned long long bars[TC_STAGES + 1];
+  __shared__ __align__(8) unsigned long long bar_full[TC_MAX_STAGES];
+  __shared__ __align__(8) unsigned long long bar_empty[TC_MAX_STAGES];
+  __shared__ __align__(8) unsigned long long bar_done;
   __shared__ uint32_t tmem_slot;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -182,6 +211,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_grouped_gemm_kernel(const Tc
   const int m0 = blockIdx.y * TC_BM;
   const int n0 = blockIdx.x * p.bn;
   const int bn = p.bn;
+  const int nst = p.n_stages;
 
   // stage layout: [A hi | A lo | B hi | B lo]
   const uint32_t a_bytes = TC_BM * TC_BK * 4;
@@ -191,65 +221,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_grouped_gemm_kernel(const Tc
   // the swizzled layout XORs absolute address bits [7,9) into [5,7): every buffer starts 1024-aligned
   char* smem = tc_smem + ((1024u - (smem_u32(tc_smem) & 1023u)) & 1023u);
 
-  // two accumulators of `acc_cols` columns: hi*hi in the first, the two correction products in the
-  // second. The tensor core truncates when it adds into an fp32 accumulator, so the error grows with
-  // the number of accumulations; keeping the 2^-11-sized corrections apart cuts that by three.
-  uint32_t acc_cols = 32;
-  while ((int)acc_cols < bn) acc_cols <<= 1;
-  const uint32_t ncols = 2 * acc_cols;
+  const int stride = tc_region_stride(bn);
+  const int n_main = tc_n_main(bn);
+  const int nkb = (p.K + TC_BK - 1) / TC_BK;
+  const int nks = (p.K + 7) >> 3;  // k-steps of 8 that carry data
 
   if (tid == 0) {
-#pragma unroll
-    for (int i = 0; i <= TC_STAGES; ++i) mbar_init(smem_u32(&bars[i]), 1);
+    for (int i = 0; i < nst; ++i) {
+      mbar_init(smem_u32(&bar_full[i]), TC_LOADER_THREADS);
+      mbar_init(smem_u32(&bar_empty[i]), 1);
+    }
+    mbar_init(smem_u32(&bar_done), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0) tmem_alloc(smem_u32(&tmem_slot), ncols);
+  if (warp == TC_MMA_WARP) tmem_alloc(smem_u32(&tmem_slot), TC_TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = tmem_slot;
 
-  const Rows RA = resolve(p.A, g);
-  const Rows RB = resolve(p.B, g);
-  const int nkb = (p.K + TC_BK - 1) / TC_BK;
-  const int npb = B_KMAJOR ? (bn >> 2) : (bn_pad >> 2);  // patches of the B tile (128/4 = 32 for A)
-  const uint32_t idesc = umma_idesc_tf32(!A_KMAJOR, !B_KMAJOR, bn);
-
-  float4 ra[4], rb[8];
-  auto load_block = [&](int kb) {
-    const int k0 = kb * TC_BK;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) ra[i] = tc_patch_load<A_KMAJOR>(RA, warp + 8 * i, lane, m0, p.M, k0, p.K);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int pp = warp + 8 * i;
-      rb[i] = (pp < npb) ? tc_patch_load<B_KMAJOR>(RB, pp, lane, n0, p.N, k0, p.K) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-  };
-
-  load_block(0);
-  for (int kb = 0; kb < nkb; ++kb) {
-    const int s = kb % TC_STAGES;
-    const int use = kb / TC_STAGES;
-    if (use > 0) mbar_wait(smem_u32(&bars[s]), (uint32_t)((use - 1) & 1));  // MMAs that read stage s are done
-    char* st = smem + (size_t)s * stage_bytes;
-    char* a_hi = st;
-    char* a_lo = st + a_bytes;
-    char* b_hi = st + 2 * a_bytes;
-    char* b_lo = b_hi + b_bytes;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) tc_split_store(a_hi, a_lo, tc_patch_offset<A_KMAJOR>(warp + 8 * i, lane), ra[i]);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int pp = warp + 8 * i;
-      if (pp < npb) tc_split_store(b_hi, b_lo, tc_patch_offset<B_KMAJOR>(pp, lane), rb[i]);
-    }
-    fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core (async proxy)
-    if (kb + 1 < nkb) load_block(kb + 1);  // next block's loads fly across the barrier and the MMAs
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      const uint32_t sa_hi = smem_u32(a_hi), sa_lo = smem_u32(a_lo), sb_hi = smem_u32(b_hi), sb_lo = smem_u32(b_lo);
+  if (warp == TC_MMA_WARP) {
+    // ===== MMA issuer: one thread =====
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_tf32(!A_KMAJOR, !B_KMAJOR, bn);
       // K-major : LBO = 128 (next 16-byte k chunk), SBO = 1024 (next 8 lines), a k-step of 8 = 256 B
       // MN-major: LBO = 4096 (next 32 lines), SBO = 512 (next 4 k), a k-step of 8 = 1024 B
       const uint32_t a_lbo = A_KMAJOR ? 128u : 4096u, a_sbo = A_KMAJOR ? 1024u : 512u;
@@ -257,83 +251,147 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_grouped_gemm_kernel(const Tc
       const uint32_t a_step = A_KMAJOR ? 256u : 1024u, b_step = B_KMAJOR ? 256u : 1024u;
       const uint32_t a_lay = A_KMAJOR ? UMMA_LAYOUT_NONE : UMMA_LAYOUT_SW128_BASE32B;
       const uint32_t b_lay = B_KMAJOR ? UMMA_LAYOUT_NONE : UMMA_LAYOUT_SW128_BASE32B;
+      int ks = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % nst;
+        mbar_wait(smem_u32(&bar_full[s]), (uint32_t)((kb / nst) & 1));
+        tc_fence_after();
+        const uint32_t sa_hi = smem_u32(smem + (size_t)s * stage_bytes);
+        const uint32_t sa_lo = sa_hi + a_bytes, sb_hi = sa_hi + 2 * a_bytes, sb_lo = sb_hi + b_bytes;
 #pragma unroll
-      for (int j = 0; j < TC_BK / 8; ++j) {
-        const uint64_t dah = umma_desc(sa_hi + j * a_step, a_lbo, a_sbo, a_lay);
-        const uint64_t dal = umma_desc(sa_lo + j * a_step, a_lbo, a_sbo, a_lay);
-        const uint64_t dbh = umma_desc(sb_hi + j * b_step, b_lbo, b_sbo, b_lay);
-        const uint64_t dbl = umma_desc(sb_lo + j * b_step, b_lbo, b_sbo, b_lay);
-        const uint32_t acc = (kb | j) ? 1u : 0u;
-        umma_tf32(tmem_d + acc_cols, dal, dbh, idesc, acc);
-        umma_tf32(tmem_d + acc_cols, dah, dbl, idesc, 1u);
-        umma_tf32(tmem_d, dah, dbh, idesc, acc);
-      }
-      umma_commit(smem_u32(&bars[s]));
-      if (kb + 1 == nkb) umma_commit(smem_u32(&bars[TC_STAGES]));
-    }
-  }
-
-  // ---- epilogue: TMEM -> registers -> fused op -> global ---------------------------------------
-  mbar_wait(smem_u32(&bars[TC_STAGES]), 0);
-  tc_fence_after();
-
-  const int q = warp & 3;        // TMEM lane quarter this warp may read
-  const int half = warp >> 2;    // warps w and w+4 share a quarter and alternate 16-column chunks
-  const int m = m0 + q * 32 + lane;
-  const bool m_ok = m < p.M;
-  const int rowid = p.cidx ? p.cidx[g] : g;
-  float* C = p.cbase + (long long)rowid * p.c_gstride + p.c_off;
-
-  float bias = 0.f;
-  if (EPI == EPI_FWD && p.bias_base && m_ok) {
-    const int brow = p.bias_idx ? p.bias_idx[g] : g;
-    bias = __ldg(p.bias_base + (long long)brow * p.bias_gstride + p.bias_off + m);
-  }
-  AdamScalars as = {};
-  float* Mo = nullptr;
-  float* Vo = nullptr;
-  if (EPI == EPI_ADAM) {
-    as = make_adam_scalars(p.step[rowid], p.lr, p.b1, p.b2, p.eps);
-    Mo = p.adam_m + (long long)rowid * p.c_gstride + p.c_off;
-    Vo = p.adam_v + (long long)rowid * p.c_gstride + p.c_off;
-  }
-  const float* S = (EPI == EPI_BWD_DATA && p.saved) ? p.saved + (long long)g * p.saved_gstride : nullptr;
-
-  for (int c = half; c < (bn >> 4); c += 2) {
-    float v[16], vc[16];
-    tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 16), v);
-    tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + acc_cols + (uint32_t)(c * 16), vc);
-#pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] += vc[j];
-    const int nb = n0 + c * 16;
-    if (!m_ok || nb >= p.N) continue;
-    if (EPI == EPI_ADAM) {
-      float w[16], mm[16], vv[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const long long off = (long long)(nb + j) * p.ldc + m;
-        const bool ok = nb + j < p.N;
-        w[j] = ok ? C[off] : 0.f;
-        mm[j] = ok ? Mo[off] : 0.f;
-        vv[j] = ok ? Vo[off] : 0.f;
-      }
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        if (nb + j < p.N) {
-          const long long off = (long long)(nb + j) * p.ldc + m;
-          adam_update(w[j], mm[j], vv[j], v[j], as);
-          C[off] = w[j]; Mo[off] = mm[j]; Vo[off] = vv[j];
+        for (int j = 0; j < TC_BK / 8; ++j) {
+          if (ks < nks) {
+            const uint64_t dah = umma_desc(sa_hi + j * a_step, a_lbo, a_sbo, a_lay);
+            const uint64_t dal = umma_desc(sa_lo + j * a_step, a_lbo, a_sbo, a_lay);
+            const uint64_t dbh = umma_desc(sb_hi + j * b_step, b_lbo, b_sbo, b_lay);
+            const uint64_t dbl = umma_desc(sb_lo + j * b_step, b_lbo, b_sbo, b_lay);
+            const uint32_t main_col = (uint32_t)((1 + ks % n_main) * stride);
+            umma_tf32(tmem_d, dal, dbh, idesc, ks > 0 ? 1u : 0u);
+            umma_tf32(tmem_d, dah, dbl, idesc, 1u);
+            umma_tf32(tmem_d + main_col, dah, dbh, idesc, ks >= n_main ? 1u : 0u);
+            ++ks;
+          }
         }
+        umma_commit(smem_u32(&bar_empty[s]));
       }
-    } else {
+      umma_commit(smem_u32(&bar_done));
+    }
+    __syncwarp();
+  } else {
+    // ===== loader warps: global -> registers (two k-blocks in flight) -> split -> shared =====
+    const Rows RA = resolve(p.A, g);
+    const Rows RB = resolve(p.B, g);
+    const int npb = bn_pad >> 2;  // patches of the B tile (K-major tiles beyond bn are zero-filled)
+    float4 ra0[4], rb0[NB], ra1[4], rb1[NB];
+    auto load_block = [&](int kb, float4 (&ra)[4], float4 (&rb)[NB]) {
+      const int k0 = kb * TC_BK;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        if (nb + j < p.N) {
+      for (int i = 0; i < 4; ++i) ra[i] = tc_patch_load<A_KMAJOR>(RA, warp + 8 * i, lane, m0, p.M, k0, p.K);
+#pragma unroll
+      for (int i = 0; i < NB; ++i) {
+        const int pp = warp + 8 * i;
+        rb[i] = (pp < npb) ? tc_patch_load<B_KMAJOR>(RB, pp, lane, n0, p.N, k0, p.K) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    auto store_block = [&](int kb, const float4 (&ra)[4], const float4 (&rb)[NB]) {
+      const int s = kb % nst;
+      const int use = kb / nst;
+      if (use > 0) mbar_wait(smem_u32(&bar_empty[s]), (uint32_t)((use - 1) & 1));  // MMAs that read stage s are done
+      char* a_hi = smem + (size_t)s * stage_bytes;
+      char* a_lo = a_hi + a_bytes;
+      char* b_hi = a_hi + 2 * a_bytes;
+      char* b_lo = b_hi + b_bytes;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) tc_split_store(a_hi, a_lo, tc_patch_offset<A_KMAJOR>(warp + 8 * i, lane), ra[i]);
+#pragma unroll
+      for (int i = 0; i < NB; ++i) {
+        const int pp = warp + 8 * i;
+        if (pp < npb) tc_split_store(b_hi, b_lo, tc_patch_offset<B_KMAJOR>(pp, lane), rb[i]);
+      }
+      fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core (async proxy)
+      mbar_arrive(smem_u32(&bar_full[s]));
+    };
+    load_block(0, ra0, rb0);
+    if (nkb > 1) load_block(1, ra1, rb1);
+    for (int kb = 0; kb < nkb; kb += 2) {
+      store_block(kb, ra0, rb0);
+      if (kb + 2 < nkb) load_block(kb + 2, ra0, rb0);
+      if (kb + 1 < nkb) {
+        store_block(kb + 1, ra1, rb1);
+        if (kb + 3 < nkb) load_block(kb + 3, ra1, rb1);
+      }
+    }
+
+    // ===== epilogue: TMEM -> registers -> fused op -> global =====
+    mbar_wait(smem_u32(&bar_done), 0);
+    tc_fence_after();
+
+    const int q = warp & 3;        // TMEM lane quarter this warp may read
+    const int half = warp >> 2;    // warps w and w+4 share a quarter and alternate 16-column chunks
+    const int m = m0 + q * 32 + lane;
+    const bool m_ok = m < p.M;
+    const int rowid = p.cidx ? p.cidx[g] : g;
+    float* C = p.cbase + (long long)rowid * p.c_gstride + p.c_off;
+    const int n_used = nks < n_main ? nks : n_main;
+
+    float bias = 0.f;
+    if (EPI == EPI_FWD && p.bias_base && m_ok) {
+      const int brow = p.bias_idx ? p.bias_idx[g] : g;
+      bias = __ldg(p.bias_base + (long long)brow * p.bias_gstride + p.bias_off + m);
+    }
+    AdamScalars as = {};
+    float* Mo = nullptr;
+    float* Vo = nullptr;
+    if (EPI == EPI_ADAM) {
+      as = make_adam_scalars(p.step[rowid], p.lr, p.b1, p.b2, p.eps);
+      Mo = p.adam_m + (long long)rowid * p.c_gstride + p.c_off;
+      Vo = p.adam_v + (long long)rowid * p.c_gstride + p.c_off;
+    }
+    const float* S = (EPI == EPI_BWD_DATA && p.saved) ? p.saved + (long long)g * p.saved_gstride : nullptr;
+
+    for (int c = half; c < (bn >> 4); c += 2) {
+      const int nb = n0 + c * 16;
+      if (nb >= p.N) break;  // warp-uniform
+      const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 16);
+      float v[16], t[16];
+      tmem_ld16(taddr + (uint32_t)stride, v);  // main regions first, the small correction last
+      for (int r = 2; r <= n_used; ++r) {
+        tmem_ld16(taddr + (uint32_t)(r * stride), t);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] += t[j];
+      }
+      tmem_ld16(taddr, t);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] += t[j];
+      if (!m_ok) continue;
+      if (EPI == EPI_ADAM) {
+        float w[16], mm[16], vv[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
           const long long off = (long long)(nb + j) * p.ldc + m;
-          float o = v[j];
-          if (EPI == EPI_FWD) o = act_fwd(o + bias, p.act, p.slope);
-          if (EPI == EPI_BWD_DATA && S) o *= act_bwd_from_out(__ldg(S + off), p.act, p.slope);
-          C[off] = o;
+          const bool ok = nb + j < p.N;
+          w[j] = ok ? C[off] : 0.f;
+          mm[j] = ok ? Mo[off] : 0.f;
+          vv[j] = ok ? Vo[off] : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          if (nb + j < p.N) {
+            const long long off = (long long)(nb + j) * p.ldc + m;
+            adam_update(w[j], mm[j], vv[j], v[j], as);
+            C[off] = w[j]; Mo[off] = mm[j]; Vo[off] = vv[j];
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          if (nb + j < p.N) {
+            const long long off = (long long)(nb + j) * p.ldc + m;
+            float o = v[j];
+            if (EPI == EPI_FWD) o = act_fwd(o + bias, p.act, p.slope);
+            if (EPI == EPI_BWD_DATA && S) o *= act_bwd_from_out(__ldg(S + off), p.act, p.slope);
+            C[off] = o;
+          }
         }
       }
     }
@@ -341,34 +399,54 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_grouped_gemm_kernel(const Tc
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_d, ncols);
+  if (warp == TC_MMA_WARP) tmem_dealloc(tmem_d, TC_TMEM_COLS);
 }
 
-static inline int tc_pick_bn(int N) {
-  const int tiles = (N + TC_MAX_BN - 1) / TC_MAX_BN;
-  const int per = (N + tiles - 1) / tiles;
-  return (per + 15) / 16 * 16;
+// N tile: the largest balanced tile (multiple of 16, <= 256) whose TMEM plan keeps every hi*hi region
+// at or below TC_MAX_ACCUM accumulations for this K.
+static inline int tc_pick_bn(int N, int K) {
+  const int nks = (K + 7) / 8;
+  int need = (nks + TC_MAX_ACCUM - 1) / TC_MAX_ACCUM;
+  if (need > TC_MAX_MAIN) need = TC_MAX_MAIN;
+  for (int tiles = (N + TC_MAX_BN - 1) / TC_MAX_BN;; ++tiles) {
+    const int per = (N + tiles - 1) / tiles;
+    const int bn = (per + 15) / 16 * 16;
+    if (tc_n_main(bn) >= need || bn <= 32) return bn;
+  }
 }
-static inline size_t tc_smem_bytes(int bn) {
+static inline size_t tc_stage_bytes(int bn) {
   const size_t bn_pad = ((size_t)bn + 31) & ~(size_t)31;
-  return (size_t)TC_STAGES * (2 * TC_BM * TC_BK * 4 + 2 * bn_pad * TC_BK * 4) + 1024;
+  return 2 * TC_BM * TC_BK * 4 + 2 * bn_pad * TC_BK * 4;
+}
+constexpr size_t TC_SMEM_BUDGET = 225 * 1024;  // of the 227 KB a CTA may use; static barriers take the rest
+static inline int tc_pick_stages(int bn) {
+  int n = (int)((TC_SMEM_BUDGET - 1024) / tc_stage_bytes(bn));
+  return n > TC_MAX_STAGES ? TC_MAX_STAGES : (n < 2 ? 2 : n);
+}
+
+template <bool A_KMAJOR, bool B_KMAJOR, int EPI, int NB>
+static inline cudaError_t launch_tc_gemm_nb(const TcParams& p, int G, cudaStream_t stream) {
+  static bool attr_set = false;  // per template instantiation
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(tc_grouped_gemm_kernel<A_KMAJOR, B_KMAJOR, EPI, NB>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BUDGET);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const size_t smem = (size_t)p.n_stages * tc_stage_bytes(p.bn) + 1024;
+  dim3 grid((p.N + p.bn - 1) / p.bn, (p.M + TC_BM - 1) / TC_BM, G);
+  tc_grouped_gemm_kernel<A_KMAJOR, B_KMAJOR, EPI, NB><<<grid, TC_THREADS, smem, stream>>>(p);
+  count_launch();
+  return cudaGetLastError();
 }
 
 template <bool A_KMAJOR, bool B_KMAJOR, int EPI>
 static inline cudaError_t launch_tc_gemm(TcParams p, int G, cudaStream_t stream) {
   if (G <= 0 || p.M <= 0 || p.N <= 0) return cudaSuccess;
-  p.bn = tc_pick_bn(p.N);
-  const size_t smem = tc_smem_bytes(p.bn);
-  static bool attr_set = false;  // per template instantiation
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tc_grouped_gemm_kernel<A_KMAJOR, B_KMAJOR, EPI>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(TC_MAX_BN));
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
-  dim3 grid((p.N + p.bn - 1) / p.bn, (p.M + TC_BM - 1) / TC_BM, G);
-  tc_grouped_gemm_kernel<A_KMAJOR, B_KMAJOR, EPI><<<grid, TC_THREADS, smem, stream>>>(p);
-  return cudaGetLastError();
+  p.bn = tc_pick_bn(p.N, p.K);
+  p.n_stages = tc_pick_stages(p.bn);
+  if (p.bn <= 128) return launch_tc_gemm_nb<A_KMAJOR, B_KMAJOR, EPI, 4>(p, G, stream);
+  return launch_tc_gemm_nb<A_KMAJOR, B_KMAJOR, EPI, 8>(p, G, stream);
 }
 
 // The tensor-core path needs float4-addressable operands: 16-byte aligned bases / strides, the

@@ -22,7 +22,7 @@ import torch
 import torch.nn.functional as F
 
 from . import abi
-from .engine import ClientBank, adam_rows
+from .engine import ClientBank, _stream
 from .generators import StackedGenerator
 from .partition import assign_clients
 
@@ -99,6 +99,7 @@ class MDStyleSim:
         self.weighting = spec["weighting"]
         self.client_list, _ = assign_clients(self.C, self.S)
         self.server_of = torch.arange(self.C, device=self.device, dtype=torch.int32) // self.N
+        self.srv_ptr = torch.arange(0, self.C + 1, self.N, device=self.device, dtype=torch.int32)
         # beta: client share of its server's data; A: server share of all data (CGLGAN/2DMG/main.py:184-188,117-122)
         if part_sizes is None:
             part_sizes = [1] * self.C
@@ -148,15 +149,12 @@ class MDStyleSim:
         if z_g is None:
             z_g = torch.randn(S, B, 100, device=self.device)
         G = self.G
-        with torch.no_grad():
-            Xd = G(z_d)
-        Xg = G(z_g)
+        Xd = G(z_d)          # no_grad pass of the reference: only its BatchNorm running statistics survive
+        Xg = G(z_g)          # the pass the generator is trained through
         shared = not self.multi_head
-        if shared and self.n_heads == 1:      # CGLGAN iid==0: Generator(ims, 1), one head shared by all
+        if shared:           # one batch per server, seen by all of its clients (CGLGAN iid==0: Generator(ims, 1))
             Xd, Xg_flat = Xd.reshape(S, B, d), Xg.reshape(S, B, d)
-        elif shared:
-            Xg_flat = Xg.reshape(S, B, d)
-        else:
+        else:                # head i of server s feeds client s*N+i
             Xd, Xg_flat = Xd.reshape(S * N, B, d), Xg.reshape(S * N, B, d)
         idx = self.server_of if shared else None
         if self.profile:
@@ -165,23 +163,26 @@ class MDStyleSim:
         for e in range(real.shape[0]):
             self.last_d_loss = self.bank.d_step(real[e], Xd, n_real=None if n_real is None else n_real[e],
                                                 fake_idx=idx)
-        loss = self.bank.g_loss(Xg_flat, xg_idx=idx).view(S, N)
+        loss, dxg = self.bank.g_loss_raw(Xg_flat, xg_idx=idx)
+        loss = loss.view(S, N)
         if self.profile:
             ev1 = torch.cuda.Event(enable_timing=True)
             ev1.record()
             self._events.append((ev0, ev1))
-        w = self._server_weights(loss.detach())
-        G.zero_grad()
+        w = self._server_weights(loss)
         if self.multi_head:
             # heads: d(sum_i loss_i); trunk: d(sum_i w_i loss_i)  (CGLGAN/2DMG/main.py:254-269, mixed-gan.py:263-281)
-            G.trunk_scale["w"] = w.view(S, N, 1, 1)
-            loss.sum().backward()
-            G.trunk_scale["w"] = None
+            G.backward_step(dxg.view(S, N, B, d), trunk_w=w)
         else:
-            (w * loss).sum().backward()
-        G.adam_step()
+            # F_max.backward() through a shared Xg: every client's dLoss/dXg, weighted, summed per server
+            dy = torch.empty(S, B, d, device=self.device)
+            wf = w.reshape(-1).contiguous().float()
+            abi.check(abi.lib.cgl_dxg_reduce(S, abi.ptr(self.srv_ptr), None, abi.ptr(wf), abi.ptr(dxg), B * d,
+                                             abi.ptr(dy), _stream()))
+            self.bank.launches += 1
+            G.backward_step(dy.view(S, 1, B, d) if self.n_heads else dy)
         self.t += 1
-        return loss.detach()
+        return loss
 
     def _server_weights(self, loss):
         """Per-client weight of its G loss in the server objective; also advances Lambda."""
@@ -255,8 +256,6 @@ class MDStyleSim:
 
 
 def _wsum(w, rows, buf, ld, out, comm):
-    from .engine import _stream
-    import ctypes as C
     w = w.contiguous()
     if comm is None:
         abi.check(abi.lib.cgl_wsum(w.numel(), ld, abi.ptr(w), abi.ptr(rows), abi.ptr(buf), ld, abi.ptr(out), _stream()))
@@ -266,7 +265,6 @@ def _wsum(w, rows, buf, ld, out, comm):
 
 
 def _bcast(rows, sigma, g, buf, ld, rows_n=None):
-    from .engine import _stream
     R = rows.numel() if rows is not None else rows_n
     abi.check(abi.lib.cgl_bcast_mix(R, ld, abi.ptr(rows), float(sigma), abi.ptr(g), abi.ptr(buf), ld, _stream()))
 
@@ -308,15 +306,12 @@ class FLStyleSim:
         if z_g is None:
             z_g = torch.randn(C, B, 100, device=self.device)
         G = self.G
-        with torch.no_grad():   # the G grads D_loss.backward() leaves behind are zeroed at flgan.py:264
-            Xd = G(z_d)
+        Xd = G(z_d)   # the G grads D_loss.backward() leaves behind are zeroed at flgan.py:264: a plain forward
         d_loss = self.bank.d_step(real, Xd.reshape(C, B, self.d), n_real=n_real)
-        G.zero_grad()
         Xg = G(z_g)
-        g_loss = self.bank.g_loss(Xg.reshape(C, B, self.d))
-        g_loss.sum().backward()
-        G.adam_step()
-        return d_loss, g_loss.detach()
+        g_loss, dxg = self.bank.g_loss_raw(Xg.reshape(C, B, self.d))
+        G.backward_step(dxg)     # g_loss.backward(); opti_g.step()  (flgan.py:266-269)
+        return d_loss, g_loss
 
     def aggregate(self):
         """Server.run: uniform (or weighted) average of every client's G and D, loaded back into every

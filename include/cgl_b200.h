@@ -96,6 +96,8 @@ const char* cgl_version(void);
 const char* cgl_last_error(void);
 /* 1 if a CUDA device with compute capability 10.x is usable, 0 otherwise (never fails). */
 int cgl_device_ok(void);
+/* Number of CUDA kernels this library has launched in this process (bench.py's gpu_launches). */
+long long cgl_launch_count(void);
 
 /* Replaces: the model constructors (a6) as far as shapes go. */
 int cgl_arch_describe(int arch_id, cgl_mlp_desc* out_desc);
@@ -136,6 +138,31 @@ int cgl_g_loss(const cgl_mlp_desc* arch, int G, const float* params, int64_t ldp
 int cgl_dxg_reduce(int S, const int32_t* srv_ptr, const int32_t* clients, const float* weights,
                    const float* dxg, int64_t n /* B*d floats per client */, float* out,
                    cgl_stream_t stream);
+
+/* ---- the generator side of a round (a4, a5) ---------------------------------------------------------
+ * A stack of Linear [+ BatchNorm1d(eps 0.8, batch statistics)] + LeakyReLU/Tanh/Sigmoid layers over G
+ * independent groups (edge servers, generator heads, FL clients), parameters in packed rows.
+ *   row  = ids ? ids[g] : g                      (row of params / adam_* / step / bn_stats)
+ *   x[g] = x + (x_idx ? x_idx[g] : g) * x_gstride,  [rows, dims[0]]     (heads read their server's trunk output)
+ * cgl_mlp_forward: y[g] = net_row(x[g]), [G, rows, dims[L]]. train != 0: BatchNorm uses the batch statistics and
+ *   updates running_mean / running_var in bn_stats (both generator passes of Server.train do,
+ *   CGLGAN/2DMG/main.py:229-234); train == 0: running statistics (G.eval() snapshots, :217-223).
+ *   The activations needed by the backward stay in `workspace` until the next forward on it.
+ * cgl_mlp_backward: given dy = dLoss/dy of the LAST forward on `workspace`, back-propagates through every layer
+ *   (model/mnist_model.py:17-24), takes one Adam step on every parameter of the row (opti_g.step(),
+ *   CGLGAN/2DMG/main.py:276; step[row] += 1) and, if dx != NULL, writes dLoss/dx [G, rows, dims[0]]
+ *   (the heads' gradient into the shared trunk, mixed-gan.py:263-281).
+ * Replaces: Xd = net_g(z) / Xg = net_g(z) (CGLGAN/2DMG/main.py:229-234, mixed-gan.py:241-252), the generator part
+ * of F_max.backward() and opti.step() (:266-276); FL: FLGAN/MNIST/flgan.py:251-252,263-269.                  */
+size_t cgl_mlp_workspace_bytes(const cgl_mlp_desc* arch, int G, int rows);
+int cgl_mlp_forward(const cgl_mlp_desc* arch, int G, const float* params, int64_t ldp, const int32_t* ids,
+                    float* bn_stats, int64_t ld_stats, int train, const float* x, int64_t x_gstride,
+                    const int32_t* x_idx, int rows, float* y, void* workspace, size_t workspace_bytes,
+                    cgl_stream_t stream);
+int cgl_mlp_backward(const cgl_mlp_desc* arch, int G, float* params, float* adam_m, float* adam_v, int64_t ldp,
+                     int32_t* step, const int32_t* ids, const cgl_train_cfg* cfg /* lr, beta1, beta2, eps */,
+                     const float* x, int64_t x_gstride, const int32_t* x_idx, int rows, const float* y,
+                     const float* dy, float* dx, void* workspace, size_t workspace_bytes, cgl_stream_t stream);
 
 /* ---- fused Adam over packed rows (server-side G, a7) ------------------------------------
  * torch.optim.Adam(betas=(b1,b2)) semantics, CGLGAN/2DMG/main.py:192. step[r] is incremented.

@@ -51,7 +51,7 @@ def quantile_err(a, b, q=0.9, floor=0.0):
     return (e.kthvalue(k + 1).values / b.abs().max().clamp_min(max(floor, 1e-30))).item()
 
 
-def assert_params_close(a, b, lr=2e-4, steps=1, tag="", strict=True):
+def assert_params_close(a, b, lr=2e-4, steps=1, tag="", strict=True, bulk=1e-5):
     """The parameter bar of BASELINE.json ("fp32 parameters within 1e-5 relative"), stated so that the
     reference passes it against itself:
       * bulk: the 90th percentile of |a-b| is within 1e-5 * max|ref|; with strict=True (one Adam step of a
@@ -70,7 +70,7 @@ def assert_params_close(a, b, lr=2e-4, steps=1, tag="", strict=True):
     q, em = quantile_err(a, b, 0.9, floor), max_abs(a, b)
     scale = max(b.detach().double().norm().item(), floor * b.numel() ** 0.5)
     e2 = (a.detach().double().cpu() - b.detach().double().cpu()).norm().item() / scale
-    assert q <= 1e-5, (tag, "q90 relative error", q)
+    assert q <= bulk, (tag, "q90 relative error", q, "bar", bulk)
     assert e2 < (1e-4 if strict else 1e-3), (tag, "rel_l2", e2)
     assert em <= 2.2 * lr * steps, (tag, "max_abs", em)
     if strict:
@@ -88,6 +88,17 @@ def assert_rows_close(a, b, tag="", row_frac=0.97, tol=1e-5):
     ok = (row_err <= tol).double().mean().item()
     assert ok >= row_frac, (tag, "rows within tol", tol, ok)
     assert rel_l2(a, b) < 5e-2, (tag, "rel_l2", rel_l2(a, b))
+
+
+def assert_grad_close(a, b, tag="", tol=1e-4, elem_frac=0.99, l2=2e-2):
+    """dLoss/dXg AFTER Adam steps: the two discriminators differ at the ill-conditioned elements (see
+    assert_params_close). One flipped first-layer weight moves a whole COLUMN of dLoss/dXg, one LeakyReLU kink
+    flip a whole ROW; everything else agrees to fp32 rounding. So: >= 99 % of the elements within 1e-4 of the
+    tensor's scale, and a bounded L2 distance."""
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    ok = ((a - b).abs() <= tol * b.abs().max().clamp_min(1e-30)).double().mean().item()
+    assert ok >= elem_frac, (tag, "elements within tol", tol, ok)
+    assert rel_l2(a, b) < l2, (tag, "rel_l2", rel_l2(a, b))
 
 
 def bn_fed_biases(module):

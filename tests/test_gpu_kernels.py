@@ -5,7 +5,7 @@ import random
 import pytest
 import torch
 
-from helpers import D_IN, assert_params_close, assert_rows_close, make_batches, make_ds, rel_err, rel_l2, osteps
+from helpers import D_IN, assert_grad_close, assert_params_close, assert_rows_close, make_batches, make_ds, rel_err, rel_l2, osteps
 
 pytestmark = pytest.mark.gpu
 
@@ -56,9 +56,8 @@ def test_d_step_and_g_loss_match_oracle(lib, arch, scale, steps):
             l_ref.backward()
             assert abs(d_gpu[g].item() - d_ref.item()) < LOSS_TOL, (it, g, d_gpu[g].item(), d_ref.item())
             assert abs(l_gpu[g].item() - l_ref.item()) < LOSS_TOL, (it, g)
-            # after an Adam step the two D's differ at the ill-conditioned elements (see assert_params_close),
-            # and a sample whose pre-activation sits on the LeakyReLU kink flips a whole row of dLoss/dXg
-            assert_rows_close(xg_dev.grad[g], x.grad, tag=(it, g), row_frac=0.9, tol=1e-4)
+            # after an Adam step the two D's differ at the ill-conditioned elements (see assert_grad_close)
+            assert_grad_close(xg_dev.grad[g], x.grad, tag=(it, g))
     for g in range(G):
         # layer-wise (a small layer must not hide behind a large one)
         off = 0
@@ -102,38 +101,51 @@ def test_d_step_indexed_clients_and_shared_fake(lib):
     assert rel_l2(xg_dev.grad, x.grad) < 1e-3
 
 
-def test_linear_blocks_against_torch(lib):
-    """Grouped Linear fwd / bwd-data / wgrad for ragged shapes (not multiples of the 128x128x16 tile)."""
+@pytest.mark.parametrize("mode,tol", [(1, 2e-6), (2, 6e-6)])
+def test_linear_blocks_against_torch(lib, mode, tol):
+    """Grouped Linear fwd / bwd-data / wgrad for ragged shapes (not multiples of the tiles) on both GEMM kernels:
+    mode 1 = FFMA (exact fp32 products), mode 2 = tcgen05 3xTF32 wherever the operands are float4-addressable
+    (its fp32 accumulator truncates: ~2.4e-9 * K relative, see csrc/tc_gemm.cuh). float64 reference."""
     import ctypes as C
     from cgl_gan_b200 import abi
+    abi.check(abi.lib.cgl_set_gemm_mode(mode))
+    try:
+        _linear_blocks(abi, tol)
+    finally:
+        abi.check(abi.lib.cgl_set_gemm_mode(0))
+
+
+def _linear_blocks(abi, TOL):
+    import ctypes as C
     torch.manual_seed(0)
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-    for (G, rows, din, dout) in [(3, 100, 100, 32), (2, 200, 2, 128), (2, 37, 130, 257), (1, 300, 784, 512)]:
+    for (G, rows, din, dout) in [(3, 100, 100, 32), (2, 200, 2, 128), (2, 37, 130, 257), (1, 300, 784, 512),
+                                 (2, 100, 512, 1024), (2, 200, 512, 256), (1, 260, 132, 264), (2, 100, 1024, 784)]:
         ld = (din * dout + dout + 31) // 32 * 32
         prm = torch.randn(G, ld) * 0.1
         x = torch.randn(G, rows, din)
         dy = torch.randn(G, rows, dout)
         W = prm[:, :din * dout].view(G, dout, din)
         b = prm[:, din * dout:din * dout + dout]
-        y_ref = torch.nn.functional.leaky_relu(torch.baddbmm(b.unsqueeze(1), x, W.transpose(1, 2)), 0.2)
+        y_ref = torch.nn.functional.leaky_relu(torch.baddbmm(b.double().unsqueeze(1), x.double(), W.double().transpose(1, 2)), 0.2)
         prm_d, x_d, dy_d = prm.cuda(), x.cuda(), dy.cuda()
         y = torch.empty(G, rows, dout, device="cuda")
         abi.check(abi.lib.cgl_linear_fwd(G, rows, din, dout, abi.ptr(x_d), rows * din, abi.ptr(prm_d), ld, None, 0,
                                          din * dout, abi.ACT_LRELU, 0.2, abi.ptr(y), rows * dout, st))
-        assert rel_err(y, y_ref) < 2e-6, (G, rows, din, dout, rel_err(y, y_ref))
+        assert rel_err(y, y_ref) < TOL, (G, rows, din, dout, rel_err(y, y_ref))
         dx = torch.empty(G, rows, din, device="cuda")
         saved = torch.randn(G, rows, din)
         abi.check(abi.lib.cgl_linear_bwd_data(G, rows, din, dout, abi.ptr(dy_d), rows * dout, abi.ptr(prm_d), ld, None,
                                               0, abi.ptr(saved.cuda()), rows * din, abi.ACT_LRELU, 0.2, abi.ptr(dx),
                                               rows * din, st))
-        dx_ref = torch.bmm(dy, W) * torch.where(saved > 0, 1.0, 0.2)
-        assert rel_err(dx, dx_ref) < 2e-6, (G, rows, din, dout)
+        dx_ref = torch.bmm(dy.double(), W.double()) * torch.where(saved > 0, 1.0, 0.2)
+        assert rel_err(dx, dx_ref) < TOL, (G, rows, din, dout, rel_err(dx, dx_ref))
         grad = torch.zeros(G, ld, device="cuda")
         abi.check(abi.lib.cgl_linear_wgrad(G, rows, din, dout, abi.ptr(dy_d), rows * dout, abi.ptr(x_d), rows * din,
                                            abi.ptr(grad), ld, None, 0, din * dout, st))
-        dW_ref = torch.bmm(dy.transpose(1, 2), x).reshape(G, -1)
-        db_ref = dy.sum(1)
-        assert rel_err(grad[:, :din * dout], dW_ref) < 2e-6, (G, rows, din, dout)
+        dW_ref = torch.bmm(dy.double().transpose(1, 2), x.double()).reshape(G, -1)
+        db_ref = dy.double().sum(1)
+        assert rel_err(grad[:, :din * dout], dW_ref) < TOL, (G, rows, din, dout)
         assert rel_err(grad[:, din * dout:din * dout + dout], db_ref) < 2e-6
         assert torch.all(grad[:, din * dout + dout:] == 0)
 
