@@ -12,7 +12,7 @@
 // widths 784/512/256/1024 fill it, while N takes any multiple of 16 up to 256 (200 -> 208, 100 -> 112).
 //
 // Precision: the reference is strict fp32 (torch default, allow_tf32 = False). Each fp32 operand x is
-// split in registers into hi = rna_tf32(x), lo = rna_tf32(x - hi); three MMAs per k-step accumulate
+// split in registers into hi = tf32(x) (round to nearest), lo = x - hi (exact); three MMAs per k-step accumulate
 // lo*hi + hi*lo (correction region) and hi*hi (rotating main regions) in fp32 TMEM accumulators that the
 // epilogue adds up (the dropped lo*lo term is ~2^-22 relative; see "TMEM plan" below for the regions).
 // Because the split needs a register pass anyway, operands are staged global -> registers -> shared
@@ -102,10 +102,10 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-__device__ __forceinline__ float rna_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+// hi = x rounded to tf32 (10 mantissa bits), round-half-up in magnitude: two integer instructions.
+// (cvt.rna.tf32.f32 compiles to a ~10-instruction emulation on sm_100a and dominated the loader warps.)
+__device__ __forceinline__ float tf32_hi(float x) {
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
 
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor: start >> 4 in [0,14), leading byte
@@ -160,9 +160,11 @@ __device__ __forceinline__ uint32_t tc_patch_offset(int p, int lane) {
   return (uint32_t)((p >> 3) * 4096 + (p & 7) * 512 + kr * 128 + (((c16 >> 1) ^ kr) << 5) + (c16 & 1) * 16);
 }
 __device__ __forceinline__ void tc_split_store(char* hi, char* lo, uint32_t off, const float4& v) {
+  // lo = x - hi is exact in fp32 (|lo| <= 2^-11 |x|, either sign); the tensor core drops its low 13 bits,
+  // an error below 2^-21 |x| without a preferred direction relative to x
   float4 h, l;
-  h.x = rna_tf32(v.x); h.y = rna_tf32(v.y); h.z = rna_tf32(v.z); h.w = rna_tf32(v.w);
-  l.x = rna_tf32(v.x - h.x); l.y = rna_tf32(v.y - h.y); l.z = rna_tf32(v.z - h.z); l.w = rna_tf32(v.w - h.w);
+  h.x = tf32_hi(v.x); h.y = tf32_hi(v.y); h.z = tf32_hi(v.z); h.w = tf32_hi(v.w);
+  l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
   *reinterpret_cast<float4*>(hi + off) = h;
   *reinterpret_cast<float4*>(lo + off) = l;
 }
@@ -383,13 +385,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_grouped_gemm_kernel(const Tc
           }
         }
       } else {
+        if (EPI == EPI_BWD_DATA && S) {
+          // all 16 saved activations first: the stores below may alias them as far as the compiler knows,
+          // and one dependent global load per store serialises the whole epilogue on memory latency
+          float sv[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            sv[j] = (nb + j < p.N) ? __ldg(S + (long long)(nb + j) * p.ldc + m) : 0.f;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] *= act_bwd_from_out(sv[j], p.act, p.slope);
+        }
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           if (nb + j < p.N) {
             const long long off = (long long)(nb + j) * p.ldc + m;
             float o = v[j];
             if (EPI == EPI_FWD) o = act_fwd(o + bias, p.act, p.slope);
-            if (EPI == EPI_BWD_DATA && S) o *= act_bwd_from_out(__ldg(S + off), p.act, p.slope);
             C[off] = o;
           }
         }
