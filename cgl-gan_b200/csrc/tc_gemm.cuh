@@ -110,8 +110,9 @@ __device__ __forceinline__ float tf32_hi(float x) {
 
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor: start >> 4 in [0,14), leading byte
 // offset >> 4 in [16,30), stride byte offset >> 4 in [32,46), version 1 in [46,48), layout type in
-// [61,64): 0 = SWIZZLE_NONE, 1 = SWIZZLE_128B_BASE32B -- the only layout tf32 accepts MN-major).
-constexpr uint32_t UMMA_LAYOUT_NONE = 0, UMMA_LAYOUT_SW128_BASE32B = 1;
+// [61,64): 0 = SWIZZLE_NONE, 1 = SWIZZLE_128B_BASE32B -- the only layout tf32 accepts MN-major --,
+// 2 = SWIZZLE_128B).
+constexpr uint32_t UMMA_LAYOUT_NONE = 0, UMMA_LAYOUT_SW128_BASE32B = 1, UMMA_LAYOUT_SW128 = 2;
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
   uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
@@ -130,10 +131,12 @@ __host__ __device__ inline uint32_t umma_idesc_tf32(bool a_mn_major, bool b_mn_m
 // A staged tile is T (= 128, or BN rounded up to 32) lines of the M/N dimension by TC_BK = 32 of K, as
 // hi and lo copies. One warp-wide float4 access covers a "patch" whose 32 float4s land in 512
 // consecutive bytes of shared memory (conflict-free) and read whole 64/128-byte row segments.
-//   K-major  (k contiguous in global; lines = m/n), no swizzle, core matrix = 8 lines x 16 B:
-//       byte(t, k) = (t/8)*1024 + (k/4)*128 + (t%8)*16 + (k%4)*4          LBO = 128 (next 4 k), SBO = 1024 (next 8 t)
-//       patch p = 8 lines x 16 k: line group p/2, k half p%2;  lane -> (t = 8*(p/2) + lane%8, k = 16*(p%2) + 4*(lane/8))
-//       one MMA (8 k) = 2 k chunks = 256 B further
+//   K-major  (k contiguous in global; lines = m/n), SWIZZLE_128B: line t is one 128-byte row (32 k), atoms of
+//       8 rows, the 16-byte chunk index XORed with the row index (Swizzle<3,4,3> on the byte address):
+//       byte(t, k) = t*128 + (((k/4) ^ (t%8)) * 16) + (k%4)*4            SBO = 1024 (next 8 lines); LBO unused
+//       patch p = 4 lines x 32 k;  lane -> (t = 4*p + lane/8, k = 4*(lane%8)): every warp load reads four whole
+//       128-byte rows (full cache lines: the SM's outstanding-request budget is what bounds the loaders)
+//       one MMA (8 k) = 32 B further inside the swizzle span
 //   MN-major (m/n contiguous in global; lines = k), SWIZZLE_128B_BASE32B, atom = 4 k x 32 t (4 rows of 128 B,
 //       the 32-byte chunk index XORed with the row index: Swizzle<2,5,2> on the byte address):
 //       byte(t, k) = (t/32)*4096 + (k/4)*512 + (k%4)*128 + ((((t%32)/8) ^ (k%4)) * 32) + (t%8)*4
@@ -143,8 +146,8 @@ template <bool KMAJOR>
 __device__ __forceinline__ float4 tc_patch_load(const Rows& R, int p, int lane, int t0, int dimT, int k0, int dimK) {
   float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
   if (KMAJOR) {
-    const int t = t0 + 8 * (p >> 1) + (lane & 7);
-    const int k = k0 + 16 * (p & 1) + 4 * (lane >> 3);
+    const int t = t0 + 4 * p + (lane >> 3);
+    const int k = k0 + 4 * (lane & 7);
     if (t < dimT && k < dimK) v = __ldg(reinterpret_cast<const float4*>(row_ptr(R, t) + k));
   } else {
     const int k = k0 + 4 * (p & 7) + (lane >> 3);
@@ -155,7 +158,10 @@ __device__ __forceinline__ float4 tc_patch_load(const Rows& R, int p, int lane, 
 }
 template <bool KMAJOR>
 __device__ __forceinline__ uint32_t tc_patch_offset(int p, int lane) {
-  if (KMAJOR) return (uint32_t)((p >> 1) * 1024 + ((p & 1) * 4 + (lane >> 3)) * 128 + (lane & 7) * 16);
+  if (KMAJOR) {
+    const int r = 4 * p + (lane >> 3);
+    return (uint32_t)(r * 128 + (((lane & 7) ^ (r & 7)) << 4));
+  }
   const int kr = lane >> 3, c16 = lane & 7;
   return (uint32_t)((p >> 3) * 4096 + (p & 7) * 512 + kr * 128 + (((c16 >> 1) ^ kr) << 5) + (c16 & 1) * 16);
 }
@@ -246,17 +252,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_grouped_gemm_kernel(const Tc
     // ===== MMA issuer: one thread =====
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_tf32(!A_KMAJOR, !B_KMAJOR, bn);
-      // K-major : LBO = 128 (next 16-byte k chunk), SBO = 1024 (next 8 lines), a k-step of 8 = 256 B
-      // MN-major: LBO = 4096 (next 32 lines), SBO = 512 (next 4 k), a k-step of 8 = 1024 B
-      const uint32_t a_lbo = A_KMAJOR ? 128u : 4096u, a_sbo = A_KMAJOR ? 1024u : 512u;
-      const uint32_t b_lbo = B_KMAJOR ? 128u : 4096u, b_sbo = B_KMAJOR ? 1024u : 512u;
-      const uint32_t a_step = A_KMAJOR ? 256u : 1024u, b_step = B_KMAJOR ? 256u : 1024u;
-      const uint32_t a_lay = A_KMAJOR ? UMMA_LAYOUT_NONE : UMMA_LAYOUT_SW128_BASE32B;
-      const uint32_t b_lay = B_KMAJOR ? UMMA_LAYOUT_NONE : UMMA_LAYOUT_SW128_BASE32B;
-      int ks = 0;
+      // K-major : SWIZZLE_128B, SBO = 1024 (next 8 lines), LBO unused, a k-step of 8 = 32 B inside the span
+      // MN-major: SWIZZLE_128B_BASE32B, LBO = 4096 (next 32 lines), SBO = 512 (next 4 k), a k-step of 8 = 1024 B
+      const uint32_t a_lbo = A_KMAJOR ? 16u : 4096u, a_sbo = A_KMAJOR ? 1024u : 512u;
+      const uint32_t b_lbo = B_KMAJOR ? 16u : 4096u, b_sbo = B_KMAJOR ? 1024u : 512u;
+      const uint32_t a_step = A_KMAJOR ? 32u : 1024u, b_step = B_KMAJOR ? 32u : 1024u;
+      const uint32_t a_lay = A_KMAJOR ? UMMA_LAYOUT_SW128 : UMMA_LAYOUT_SW128_BASE32B;
+      const uint32_t b_lay = B_KMAJOR ? UMMA_LAYOUT_SW128 : UMMA_LAYOUT_SW128_BASE32B;
+      int ks = 0, s = 0, reg = 0;  // k-step counter, stage, main region of the next k-step
+      uint32_t par = 0;
       for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % nst;
-        mbar_wait(smem_u32(&bar_full[s]), (uint32_t)((kb / nst) & 1));
+        mbar_wait(smem_u32(&bar_full[s]), par);
         tc_fence_after();
         const uint32_t sa_hi = smem_u32(smem + (size_t)s * stage_bytes);
         const uint32_t sa_lo = sa_hi + a_bytes, sb_hi = sa_hi + 2 * a_bytes, sb_lo = sb_hi + b_bytes;
@@ -267,7 +273,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_grouped_gemm_kernel(const Tc
             const uint64_t dal = umma_desc(sa_lo + j * a_step, a_lbo, a_sbo, a_lay);
             const uint64_t dbh = umma_desc(sb_hi + j * b_step, b_lbo, b_sbo, b_lay);
             const uint64_t dbl = umma_desc(sb_lo + j * b_step, b_lbo, b_sbo, b_lay);
-            const uint32_t main_col = (uint32_t)((1 + ks % n_main) * stride);
+            const uint32_t main_col = (uint32_t)((1 + reg) * stride);
+            if (++reg == n_main) reg = 0;
             umma_tf32(tmem_d, dal, dbh, idesc, ks > 0 ? 1u : 0u);
             umma_tf32(tmem_d, dah, dbl, idesc, 1u);
             umma_tf32(tmem_d + main_col, dah, dbh, idesc, ks >= n_main ? 1u : 0u);
@@ -275,6 +282,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_grouped_gemm_kernel(const Tc
           }
         }
         umma_commit(smem_u32(&bar_empty[s]));
+        if (++s == nst) { s = 0; par ^= 1u; }
       }
       umma_commit(smem_u32(&bar_done));
     }
@@ -284,43 +292,52 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_grouped_gemm_kernel(const Tc
     const Rows RA = resolve(p.A, g);
     const Rows RB = resolve(p.B, g);
     const int npb = bn_pad >> 2;  // patches of the B tile (K-major tiles beyond bn are zero-filled)
-    float4 ra0[4], rb0[NB], ra1[4], rb1[NB];
-    auto load_block = [&](int kb, float4 (&ra)[4], float4 (&rb)[NB]) {
+    constexpr int DEPTH = (NB == 4) ? 3 : 2;  // k-blocks of global loads in flight per thread
+    float4 ra[DEPTH][4], rb[DEPTH][NB];
+    auto load_block = [&](int kb, float4 (&qa)[4], float4 (&qb)[NB]) {
       const int k0 = kb * TC_BK;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) ra[i] = tc_patch_load<A_KMAJOR>(RA, warp + 8 * i, lane, m0, p.M, k0, p.K);
+      for (int i = 0; i < 4; ++i) qa[i] = tc_patch_load<A_KMAJOR>(RA, warp + 8 * i, lane, m0, p.M, k0, p.K);
 #pragma unroll
       for (int i = 0; i < NB; ++i) {
         const int pp = warp + 8 * i;
-        rb[i] = (pp < npb) ? tc_patch_load<B_KMAJOR>(RB, pp, lane, n0, p.N, k0, p.K) : make_float4(0.f, 0.f, 0.f, 0.f);
+        qb[i] = (pp < npb) ? tc_patch_load<B_KMAJOR>(RB, pp, lane, n0, p.N, k0, p.K) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
-    auto store_block = [&](int kb, const float4 (&ra)[4], const float4 (&rb)[NB]) {
-      const int s = kb % nst;
-      const int use = kb / nst;
-      if (use > 0) mbar_wait(smem_u32(&bar_empty[s]), (uint32_t)((use - 1) & 1));  // MMAs that read stage s are done
-      char* a_hi = smem + (size_t)s * stage_bytes;
+    int st_s = 0;            // stage of the next store
+    uint32_t st_par = 1;     // parity to wait for on empty[st_s]; nothing to wait for during the first pass
+    bool st_first = true;
+    auto store_block = [&](const float4 (&qa)[4], const float4 (&qb)[NB]) {
+      if (!st_first) mbar_wait(smem_u32(&bar_empty[st_s]), st_par);  // MMAs that read this stage are done
+      char* a_hi = smem + (size_t)st_s * stage_bytes;
       char* a_lo = a_hi + a_bytes;
       char* b_hi = a_hi + 2 * a_bytes;
       char* b_lo = b_hi + b_bytes;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) tc_split_store(a_hi, a_lo, tc_patch_offset<A_KMAJOR>(warp + 8 * i, lane), ra[i]);
+      for (int i = 0; i < 4; ++i) tc_split_store(a_hi, a_lo, tc_patch_offset<A_KMAJOR>(warp + 8 * i, lane), qa[i]);
 #pragma unroll
       for (int i = 0; i < NB; ++i) {
         const int pp = warp + 8 * i;
-        if (pp < npb) tc_split_store(b_hi, b_lo, tc_patch_offset<B_KMAJOR>(pp, lane), rb[i]);
+        if (pp < npb) tc_split_store(b_hi, b_lo, tc_patch_offset<B_KMAJOR>(pp, lane), qb[i]);
       }
       fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core (async proxy)
-      mbar_arrive(smem_u32(&bar_full[s]));
+      mbar_arrive(smem_u32(&bar_full[st_s]));
+      if (++st_s == nst) {
+        st_s = 0;
+        if (st_first) { st_first = false; st_par = 0; } else { st_par ^= 1u; }
+      }
     };
-    load_block(0, ra0, rb0);
-    if (nkb > 1) load_block(1, ra1, rb1);
-    for (int kb = 0; kb < nkb; kb += 2) {
-      store_block(kb, ra0, rb0);
-      if (kb + 2 < nkb) load_block(kb + 2, ra0, rb0);
-      if (kb + 1 < nkb) {
-        store_block(kb + 1, ra1, rb1);
-        if (kb + 3 < nkb) load_block(kb + 3, ra1, rb1);
+#pragma unroll
+    for (int d = 0; d < DEPTH; ++d)
+      if (d < nkb) load_block(d, ra[d], rb[d]);
+    for (int kb0 = 0; kb0 < nkb; kb0 += DEPTH) {
+#pragma unroll
+      for (int d = 0; d < DEPTH; ++d) {
+        const int kb = kb0 + d;
+        if (kb < nkb) {
+          store_block(ra[d], rb[d]);
+          if (kb + DEPTH < nkb) load_block(kb + DEPTH, ra[d], rb[d]);
+        }
       }
     }
 
@@ -351,11 +368,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_grouped_gemm_kernel(const Tc
     }
     const float* S = (EPI == EPI_BWD_DATA && p.saved) ? p.saved + (long long)g * p.saved_gstride : nullptr;
 
-    for (int c = half; c < (bn >> 4); c += 2) {
-      const int nb = n0 + c * 16;
-      if (nb >= p.N) break;  // warp-uniform
+    const int nch = bn >> 4;
+    // accumulator chunk: 16 columns of this thread's lane, summed over the TMEM regions
+    auto tmem_chunk = [&](int c, float (&v)[16]) {
       const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 16);
-      float v[16], t[16];
+      float t[16];
       tmem_ld16(taddr + (uint32_t)stride, v);  // main regions first, the small correction last
       for (int r = 2; r <= n_used; ++r) {
         tmem_ld16(taddr + (uint32_t)(r * stride), t);
@@ -365,26 +382,52 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_grouped_gemm_kernel(const Tc
       tmem_ld16(taddr, t);
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] += t[j];
-      if (!m_ok) continue;
-      if (EPI == EPI_ADAM) {
-        float w[16], mm[16], vv[16];
+    };
+    auto chunk_ok = [&](int c) { return c < nch && n0 + c * 16 < p.N; };  // warp-uniform
+
+    if (EPI == EPI_ADAM) {
+      // W / m / v of the NEXT chunk are requested before the current chunk is updated and stored, so the
+      // ~48 loads per thread overlap the Adam arithmetic instead of serialising with it
+      float w[2][16], mm[2][16], vv[2][16];
+      auto fetch = [&](int c, float (&fw)[16], float (&fm)[16], float (&fv)[16]) {
+        const int nb = n0 + c * 16;
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const long long off = (long long)(nb + j) * p.ldc + m;
-          const bool ok = nb + j < p.N;
-          w[j] = ok ? C[off] : 0.f;
-          mm[j] = ok ? Mo[off] : 0.f;
-          vv[j] = ok ? Vo[off] : 0.f;
+          const bool ok = m_ok && nb + j < p.N;
+          fw[j] = ok ? C[off] : 0.f;
+          fm[j] = ok ? Mo[off] : 0.f;
+          fv[j] = ok ? Vo[off] : 0.f;
         }
+      };
+      auto update = [&](int c, float (&fw)[16], float (&fm)[16], float (&fv)[16], const float (&g)[16]) {
+        const int nb = n0 + c * 16;
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          if (nb + j < p.N) {
+          if (m_ok && nb + j < p.N) {
             const long long off = (long long)(nb + j) * p.ldc + m;
-            adam_update(w[j], mm[j], vv[j], v[j], as);
-            C[off] = w[j]; Mo[off] = mm[j]; Vo[off] = vv[j];
+            adam_update(fw[j], fm[j], fv[j], g[j], as);
+            C[off] = fw[j]; Mo[off] = fm[j]; Vo[off] = fv[j];
           }
         }
-      } else {
+      };
+      if (chunk_ok(half)) fetch(half, w[0], mm[0], vv[0]);
+      for (int c = half; chunk_ok(c); c += 4) {
+        float g[16];
+        tmem_chunk(c, g);
+        if (chunk_ok(c + 2)) fetch(c + 2, w[1], mm[1], vv[1]);
+        update(c, w[0], mm[0], vv[0], g);
+        if (!chunk_ok(c + 2)) break;
+        tmem_chunk(c + 2, g);
+        if (chunk_ok(c + 4)) fetch(c + 4, w[0], mm[0], vv[0]);
+        update(c + 2, w[1], mm[1], vv[1], g);
+      }
+    } else {
+      for (int c = half; chunk_ok(c); c += 2) {
+        const int nb = n0 + c * 16;
+        float v[16];
+        tmem_chunk(c, v);
+        if (!m_ok) continue;
         if (EPI == EPI_BWD_DATA && S) {
           // all 16 saved activations first: the stores below may alias them as far as the compiler knows,
           // and one dependent global load per store serialises the whole epilogue on memory latency
