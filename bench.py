@@ -262,10 +262,13 @@ def run_b200(args):
     if rank == 0:
         sampler.start()
     sim.profile = True
+    abi.profile_enable(True)          # CUDA-event pairs around every engine kernel, on the launching stream
     ms = timed(resident_round, args.steps, args.warmup)
     launches = abi.launch_count() - launch0[0]
     client_ms = sim.client_step_ms()
     sim.profile = False
+    kernels = abi.profile_summary()   # totals over warm-up + timed rounds (same work every round)
+    abi.profile_enable(False)
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e = timed(e2e_round, args.steps, args.warmup, e2e=True)
 
@@ -278,8 +281,44 @@ def run_b200(args):
     if os.path.exists(p):
         peaks = json.load(open(p))
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-    achieved = BYTES_PER_CLIENT_STEP * C / (client_ms / 1e3) / 1e9 if (client_ms and d == 784) else None
+    tf_peak = peaks.get("bf16_tflops_sustained", 1400.0)
+    peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md: 6650 GB/s, 1.4 PF sustained)"
+    rounds_profiled = args.steps + args.warmup
+    table = {}
+    for name, k in kernels.items():
+        sec = k["ms"] / 1e3
+        table[name] = {"ms_per_round": k["ms"] / rounds_profiled, "launches_per_round": k["launches"] / rounds_profiled,
+                       "ms_per_launch": k["ms"] / k["launches"],
+                       "algorithmic_GBps": (k["bytes"] / sec / 1e9) if sec > 0 else None,
+                       "algorithmic_TFLOPps": (k["flops"] / sec / 1e12) if sec > 0 else None,
+                       "bytes_per_launch": k["bytes"] / k["launches"], "flops_per_launch": k["flops"] / k["launches"]}
+    dom = max(table, key=lambda n: table[n]["ms_per_round"]) if table else None
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic_r1.json")     # dram bytes per launch from the ncu --set full capture
+    if dom and os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(dom)
+    roofline = None
+    if dom:
+        dk = table[dom]
+        hbm_bound = "wgrad+adam" in dom or dom in ("mix/aggregate", "batchnorm_fwd", "batchnorm_bwd", "head_loss", "elementwise")
+        if hbm_bound:
+            roofline = {"kernel": dom, "bound": "hbm", "achieved": dk["algorithmic_GBps"], "peak": hbm_peak, "unit": "GB/s",
+                        "frac": dk["algorithmic_GBps"] / hbm_peak, "traffic": traffic}
+        else:
+            roofline = {"kernel": dom, "bound": "tensor", "achieved": dk["algorithmic_TFLOPps"], "peak": tf_peak,
+                        "unit": "TFLOP/s", "frac": dk["algorithmic_TFLOPps"] / tf_peak, "traffic": traffic,
+                        "note": "fp32-equivalent FLOPs; the kernel issues 3 tf32 MMAs (= 6 bf16-rate units) per product"}
+        roofline.update({"peak_source": peak_src, "ms_per_launch": dk["ms_per_launch"],
+                         "share_of_round": dk["ms_per_round"] / (ms / args.steps),
+                         "bytes_per_launch": dk["bytes_per_launch"], "flops_per_launch": dk["flops_per_launch"],
+                         "timing": "cudaEvent pairs on the launching stream around every launch of this kernel class, "
+                                   "over the warm-up + timed rounds of this run"})
+    client = None
+    if client_ms and d == 784:
+        client = {"client_step_ms_per_round": client_ms, "algorithmic_bytes_per_client_step": BYTES_PER_CLIENT_STEP,
+                  "hbm_GBps": BYTES_PER_CLIENT_STEP * C / (client_ms / 1e3) / 1e9,
+                  "hbm_frac": BYTES_PER_CLIENT_STEP * C / (client_ms / 1e3) / 1e9 / hbm_peak,
+                  "fp32_TFLOPps": FLOPS_PER_CLIENT_STEP * C / (client_ms / 1e3) / 1e12}
 
     if rank == 0:
         line = {
@@ -291,13 +330,9 @@ def run_b200(args):
                     "h2d_bytes_per_step": int(C * B * d * 4 * world), "d2h_bytes_per_step": int(S * per * 4 * world)},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"kernel": "client step = cgl_d_step + cgl_g_loss (grouped FFMA GEMM chain, fused loss/backward/Adam)",
-                         "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": (achieved / hbm_peak) if achieved else None, "traffic": None,
-                         "peak_source": peak_src,
-                         "algorithmic_bytes_per_client_step": BYTES_PER_CLIENT_STEP,
-                         "client_step_ms_per_round": client_ms,
-                         "fp32_tflops_achieved": (FLOPS_PER_CLIENT_STEP * C / (client_ms / 1e3) / 1e12) if client_ms else None},
+            "roofline": roofline,
+            "client_step": client,
+            "kernels": table,
         }
         if not args.no_cpu_baseline and world == 1:
             sample = args.cpu_sample_clients

@@ -74,6 +74,11 @@ lib.cgl_mlp_workspace_bytes.restype = _sz
 lib.cgl_mlp_forward.argtypes = [C.POINTER(MlpDesc), _i32, _p, _i64, _p, _p, _i64, _i32, _p, _i64, _p, _i32, _p, _p, _sz, _p]
 lib.cgl_mlp_backward.argtypes = [C.POINTER(MlpDesc), _i32, _p, _p, _p, _i64, _p, _p, C.POINTER(TrainCfg), _p, _i64, _p,
                                  _i32, _p, _p, _p, _p, _sz, _p]
+lib.cgl_profile_enable.argtypes = [_i32]
+lib.cgl_profile_tag_name.argtypes = [_i32]
+lib.cgl_profile_tag_name.restype = C.c_char_p
+lib.cgl_profile_summary.argtypes = [_i32, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                    C.POINTER(C.c_longlong)]
 lib.cgl_set_gemm_mode.argtypes = [_i32]
 lib.cgl_get_gemm_mode.restype = C.c_int
 lib.cgl_linear_fwd.argtypes = [_i32, _i32, _i32, _i32, _p, _i64, _p, _i64, _p, _i64, _i64, _i32, _f32, _p, _i64, _p]
@@ -84,7 +89,8 @@ lib.cgl_linear_wgrad.argtypes = [_i32, _i32, _i32, _i32, _p, _i64, _p, _i64, _p,
 for _name in ("cgl_arch_describe", "cgl_mlp_layout_of", "cgl_d_step", "cgl_g_loss", "cgl_dxg_reduce",
               "cgl_adam_rows", "cgl_mix_csr", "cgl_wsum", "cgl_bcast_mix", "cgl_comm_unique_id",
               "cgl_comm_init", "cgl_comm_destroy", "cgl_allreduce_sum", "cgl_mix_allreduce",
-              "cgl_linear_fwd", "cgl_linear_bwd_data", "cgl_linear_wgrad", "cgl_set_gemm_mode", "cgl_mlp_forward", "cgl_mlp_backward"):
+              "cgl_linear_fwd", "cgl_linear_bwd_data", "cgl_linear_wgrad", "cgl_set_gemm_mode", "cgl_mlp_forward", "cgl_mlp_backward", "cgl_profile_enable",
+              "cgl_profile_summary"):
     getattr(lib, _name).restype = C.c_int
 
 
@@ -95,6 +101,25 @@ def check(rc):
 
 def version():
     return lib.cgl_version().decode()
+
+
+PROF_NUM_TAGS = 13
+
+
+def profile_enable(on=True):
+    check(lib.cgl_profile_enable(1 if on else 0))
+
+
+def profile_summary():
+    """{kernel class: dict(ms, bytes, flops, launches)} since the last profile_enable (synchronises)."""
+    out = {}
+    for tag in range(PROF_NUM_TAGS):
+        ms, by, fl, n = C.c_double(), C.c_double(), C.c_double(), C.c_longlong()
+        check(lib.cgl_profile_summary(tag, C.byref(ms), C.byref(by), C.byref(fl), C.byref(n)))
+        if n.value:
+            out[lib.cgl_profile_tag_name(tag).decode()] = dict(ms=ms.value, bytes=by.value, flops=fl.value,
+                                                               launches=n.value)
+    return out
 
 
 def launch_count():

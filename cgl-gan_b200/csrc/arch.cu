@@ -3,6 +3,7 @@
 // except cgl_device_ok().
 #include "common.cuh"
 #include <string.h>
+#include <vector>
 
 namespace cgl {
 static thread_local char g_err[512] = "";
@@ -14,11 +15,64 @@ void set_error(const char* fmt, ...) {
 }
 static long long g_launches = 0;
 void count_launch(int n) { g_launches += n; }
+
+struct ProfRec { int tag; cudaEvent_t a, b; double bytes, flops; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+static std::vector<cudaEvent_t> g_prof_pool;   // recycled events
+static cudaEvent_t prof_event() {
+  cudaEvent_t e;
+  if (!g_prof_pool.empty()) { e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+  cudaEventCreate(&e);
+  return e;
+}
+void prof_begin(int tag, double bytes, double flops, cudaStream_t st) {
+  if (!g_prof_on) return;
+  ProfRec r = {tag, prof_event(), prof_event(), bytes, flops};
+  cudaEventRecord(r.a, st);
+  g_prof.push_back(r);
+}
+void prof_end(cudaStream_t st) {
+  if (!g_prof_on || g_prof.empty()) return;
+  cudaEventRecord(g_prof.back().b, st);
+}
 }  // namespace cgl
 
 using namespace cgl;
 
 extern "C" long long cgl_launch_count(void) { return g_launches; }
+
+static const char* kProfNames[CGL_PROF_NUM_TAGS] = {
+    "linear_fwd[tcgen05]", "linear_bwd_data[tcgen05]", "linear_wgrad+adam[tcgen05]", "linear_wgrad[tcgen05]",
+    "linear_fwd[ffma]", "linear_bwd_data[ffma]", "linear_wgrad+adam[ffma]", "linear_wgrad[ffma]",
+    "head_loss", "batchnorm_fwd", "batchnorm_bwd", "mix/aggregate", "elementwise"};
+
+extern "C" int cgl_profile_enable(int on) {
+  for (auto& r : g_prof) { g_prof_pool.push_back(r.a); g_prof_pool.push_back(r.b); }
+  g_prof.clear();
+  g_prof_on = on != 0;
+  return CGL_OK;
+}
+extern "C" const char* cgl_profile_tag_name(int tag) {
+  return (tag >= 0 && tag < CGL_PROF_NUM_TAGS) ? kProfNames[tag] : "";
+}
+extern "C" int cgl_profile_summary(int tag, double* out_ms, double* out_bytes, double* out_flops, long long* out_n) {
+  CGL_REQUIRE(tag >= 0 && tag < CGL_PROF_NUM_TAGS, "bad profile tag %d", tag);
+  double ms = 0, by = 0, fl = 0;
+  long long n = 0;
+  for (auto& r : g_prof) {
+    if (r.tag != tag) continue;
+    CGL_CHECK_CUDA(cudaEventSynchronize(r.b));
+    float t = 0.f;
+    CGL_CHECK_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
+    ms += t; by += r.bytes; fl += r.flops; ++n;
+  }
+  if (out_ms) *out_ms = ms;
+  if (out_bytes) *out_bytes = by;
+  if (out_flops) *out_flops = fl;
+  if (out_n) *out_n = n;
+  return CGL_OK;
+}
 
 extern "C" const char* cgl_version(void) { return "cgl_b200 0.1.0 (sm_100a)"; }
 extern "C" const char* cgl_last_error(void) { return g_err; }

@@ -13,6 +13,15 @@ namespace cgl {
 void set_error(const char* fmt, ...);
 // every kernel launch of the library is counted (cgl_launch_count: bench.py's gpu_launches)
 void count_launch(int n = 1);
+// optional per-kernel-class timing with CUDA events on the launching stream (cgl_profile_*): bench.py's
+// roofline numbers are measured with these, live, inside the timed region
+void prof_begin(int tag, double bytes, double flops, cudaStream_t st);
+void prof_end(cudaStream_t st);
+struct ProfScope {
+  cudaStream_t st;
+  ProfScope(int tag, double bytes, double flops, cudaStream_t s) : st(s) { prof_begin(tag, bytes, flops, s); }
+  ~ProfScope() { prof_end(st); }
+};
 
 #define CGL_CHECK_CUDA(expr)                                                          \
   do {                                                                                \

@@ -273,6 +273,7 @@ static int launch_head(const cgl_mlp_desc* a, const cgl_mlp_layout& lay, int G, 
   if (smem > 48 * 1024) {
     CGL_CHECK_CUDA(cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
+  ProfScope prof(CGL_PROF_HEAD, 8.0 * G * rows * (double)h.H, 0.0, st);   // last hidden read, its gradient written
   head_kernel<<<G, HEAD_THREADS, smem, st>>>(h);
   CGL_CHECK_LAUNCH();
   return CGL_OK;

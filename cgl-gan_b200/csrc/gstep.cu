@@ -247,6 +247,7 @@ extern "C" int cgl_mlp_forward(const cgl_mlp_desc* arch, int G, const float* par
       b.eps = arch->bn_eps; b.momentum = arch->bn_momentum; b.train = train;
       b.act = arch->act[l]; b.slope = arch->lrelu_slope;
       dim3 grid((out + 127) / 128, G);
+      ProfScope prof(CGL_PROF_BN_FWD, 8.0 * G * rows * (double)out, 0.0, st);   // u read, h written
       bn_fwd_kernel<<<grid, 128, 0, st>>>(b);
       CGL_CHECK_LAUNCH();
     }
@@ -285,6 +286,7 @@ extern "C" int cgl_mlp_backward(const cgl_mlp_desc* arch, int G, float* params, 
   {
     const long long n = (long long)G * rows * arch->dims[L];
     const long long nthreads = (n + 3) / 4;
+    ProfScope prof(CGL_PROF_ELEMENTWISE, 12.0 * (double)n, 0.0, st);
     act_bwd_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, st>>>(n, dy, y, w.dZ[cur], arch->act[L - 1],
                                                                        arch->lrelu_slope);
     CGL_CHECK_LAUNCH();
@@ -303,6 +305,7 @@ extern "C" int cgl_mlp_backward(const cgl_mlp_desc* arch, int G, float* params, 
       b.gamma_off = lay.bn_w_off[l]; b.beta_off = lay.bn_b_off[l];
       b.step = step; b.lr = cfg->lr; b.b1 = cfg->beta1; b.b2 = cfg->beta2; b.eps = cfg->eps;
       dim3 grid((out + 127) / 128, G);
+      ProfScope prof(CGL_PROF_BN_BWD, 12.0 * G * rows * (double)out, 0.0, st);  // dz, u read, du written
       bn_bwd_kernel<<<grid, 128, 0, st>>>(b);
       CGL_CHECK_LAUNCH();
     }

@@ -61,7 +61,11 @@ static inline cudaError_t run_linear_fwd(int G, int rows, int in, int out, const
                                          long long ldp, const int* ids, long long w_off, long long b_off, int act,
                                          float slope, float* y, long long y_gstride, cudaStream_t st) {
   RowMap W = single_rows(params + w_off, ldp, ids, in);
-  if (tc_wanted(out, in, tc_rowmap_ok(W, in) && tc_rowmap_ok(X, in))) {
+  const bool tc = tc_wanted(out, in, tc_rowmap_ok(W, in) && tc_rowmap_ok(X, in));
+  // algorithmic traffic: W, b, x read once, y written once
+  ProfScope prof(tc ? CGL_PROF_FWD_TC : CGL_PROF_FWD_FFMA,
+                 4.0 * G * ((double)out * in + out + (double)rows * in + (double)rows * out), 2.0 * G * rows * (double)in * out, st);
+  if (tc) {
     TcParams p = {};
     p.M = out; p.N = rows; p.K = in;
     p.A = W; p.B = X;
@@ -81,7 +85,11 @@ static inline cudaError_t run_linear_bwd_data(int G, int rows, int in, int out, 
                                               float* dx, long long dx_gstride, cudaStream_t st) {
   RowMap W = single_rows(params + w_off, ldp, ids, in);
   RowMap DY = single_rows(dy, dy_gstride, nullptr, out);
-  if (tc_wanted(in, out, tc_rowmap_ok(W, in) && tc_rowmap_ok(DY, out))) {
+  const bool tc = tc_wanted(in, out, tc_rowmap_ok(W, in) && tc_rowmap_ok(DY, out));
+  ProfScope prof(tc ? CGL_PROF_BWD_TC : CGL_PROF_BWD_FFMA,
+                 4.0 * G * ((double)out * in + (double)rows * out + (saved ? 2.0 : 1.0) * rows * in),
+                 2.0 * G * rows * (double)in * out, st);
+  if (tc) {
     TcParams p = {};
     p.M = in; p.N = rows; p.K = out;
     p.A = W;   // MN-major: line = o (contraction), contiguous along i
@@ -108,7 +116,12 @@ static inline cudaError_t run_linear_wgrad(int G, int rows, int in, int out, con
                                            const RowMap& X, float* base, long long ld, const int* ids, long long w_off,
                                            long long b_off, const AdamArgs* adam, cudaStream_t st) {
   RowMap DY = single_rows(dy, dy_gstride, nullptr, out);
-  if (tc_wanted(in, rows, tc_rowmap_ok(X, in) && tc_rowmap_ok(DY, out))) {
+  const bool tc = tc_wanted(in, rows, tc_rowmap_ok(X, in) && tc_rowmap_ok(DY, out));
+  // Adam: W, m, v (and the bias triple) read and written = 24 B per parameter; x and dy read once
+  const double nparam = (double)out * in + (b_off >= 0 ? out : 0);
+  ProfScope prof(adam ? (tc ? CGL_PROF_WGRAD_ADAM_TC : CGL_PROF_WGRAD_ADAM_FFMA) : (tc ? CGL_PROF_WGRAD_TC : CGL_PROF_WGRAD_FFMA),
+                 G * ((adam ? 24.0 : 4.0) * nparam + 4.0 * rows * ((double)in + out)), 2.0 * G * rows * (double)in * out, st);
+  if (tc) {
     TcParams p = {};
     p.M = in; p.N = out; p.K = rows;
     p.A = X;   // MN-major: line = r, contiguous along i

@@ -254,6 +254,8 @@ extern "C" int cgl_mix_csr(int R, int64_t n, const int32_t* row_ptr, const int32
   cudaStream_t st = (cudaStream_t)stream;
   bool vec = aligned16(src) && aligned16(dst) && n % 4 == 0 && ld_src % 4 == 0 && ld_dst % 4 == 0;
   dim3 grid(grid_x(vec ? n / 4 : n, R), R);
+  // the column count lives on the device: at least one source row is read per written row
+  ProfScope prof(CGL_PROF_MIX, 8.0 * R * (double)n, 0.0, st);
   if (vec) mix_csr_kernel<true><<<grid, MIX_THREADS, 0, st>>>(n, row_ptr, col, vals, src, ld_src, dst, ld_dst);
   else mix_csr_kernel<false><<<grid, MIX_THREADS, 0, st>>>(n, row_ptr, col, vals, src, ld_src, dst, ld_dst);
   CGL_CHECK_LAUNCH();
@@ -269,6 +271,7 @@ extern "C" int cgl_wsum(int C, int64_t n, const float* w, const int32_t* rows, c
   bool vec = aligned16(src) && aligned16(out) && n % 4 == 0 && ld_src % 4 == 0;
   long long items = vec ? n / 4 : n;
   int gx = (int)((items + MIX_THREADS - 1) / MIX_THREADS);
+  ProfScope prof(CGL_PROF_MIX, 4.0 * ((double)C + 1.0) * (double)n, 2.0 * C * (double)n, st);   // 4 P (C_in + R_out)
   if (vec) wsum_kernel<true><<<gx, MIX_THREADS, 0, st>>>(C, n, w, rows, src, ld_src, out);
   else wsum_kernel<false><<<gx, MIX_THREADS, 0, st>>>(C, n, w, rows, src, ld_src, out);
   CGL_CHECK_LAUNCH();
@@ -286,6 +289,7 @@ extern "C" int cgl_bcast_mix(int R, int64_t n, const int32_t* rows, float sigma,
   // torch evaluates (1 - segema) in the tensor dtype (fp32) when segema is a tensor, in double
   // when it is a python float; both round to the same fp32 for the reference's 0 / 0.5 / 1.
   float oms = (float)(1.0 - (double)sigma);
+  ProfScope prof(CGL_PROF_MIX, 4.0 * (double)n * ((sigma != 0.f ? 2.0 : 1.0) * R + 1.0), 0.0, st);
   if (vec) bcast_mix_kernel<true><<<grid, MIX_THREADS, 0, st>>>(n, rows, sigma, oms, g, dst, ld_dst);
   else bcast_mix_kernel<false><<<grid, MIX_THREADS, 0, st>>>(n, rows, sigma, oms, g, dst, ld_dst);
   CGL_CHECK_LAUNCH();
@@ -316,6 +320,7 @@ extern "C" int cgl_dxg_reduce(int S, const int32_t* srv_ptr, const int32_t* clie
   cudaStream_t st = (cudaStream_t)stream;
   bool vec = aligned16(dxg) && aligned16(out) && n % 4 == 0;
   dim3 grid(grid_x(vec ? n / 4 : n, S), S);
+  ProfScope prof(CGL_PROF_ELEMENTWISE, 0.0, 0.0, st);
   if (vec) dxg_reduce_kernel<true><<<grid, MIX_THREADS, 0, st>>>(n, srv_ptr, clients, weights, dxg, out);
   else dxg_reduce_kernel<false><<<grid, MIX_THREADS, 0, st>>>(n, srv_ptr, clients, weights, dxg, out);
   CGL_CHECK_LAUNCH();

@@ -178,8 +178,10 @@ __device__ __forceinline__ void tc_split_store(char* hi, char* lo, uint32_t off,
 // EPI_* as in gemm.cuh. Output element (m, n) lives at C + n*ldc + m.
 struct TcParams {
   int M, N, K;
-  int bn;        // N tile (multiple of 16, <= 256)
-  int n_stages;  // shared-memory stages (2..TC_MAX_STAGES)
+  int bn;         // N tile (multiple of 16, <= 256)
+  int n_stages;   // shared-memory stages (1..TC_MAX_STAGES)
+  int n_main;     // hi*hi accumulator regions (see "TMEM plan")
+  int tmem_cols;  // TMEM columns to allocate: power of two >= (n_main + 1) * round_up(bn, 32)
   RowMap A, B;
   float* cbase; long long c_gstride; const int* cidx; long long c_off; int ldc;
   const float* bias_base; long long bias_gstride; const int* bias_idx; long long bias_off;  // bias[m] (EPI_FWD)
@@ -206,8 +208,10 @@ __host__ __device__ inline int tc_n_main(int bn) {
 }
 
 // NB = B patches per loader warp (4: bn <= 128, 8: bn <= 256); 8 loader warps + 1 MMA warp.
-template <bool A_KMAJOR, bool B_KMAJOR, int EPI, int NB>
-__global__ void __launch_bounds__(TC_THREADS, 1) tc_grouped_gemm_kernel(const TcParams p) {
+// OCC = CTAs per SM the variant is built for. OCC 2 (short-K weight gradients: one stage, half of TMEM, fewer
+// registers) lets one CTA's HBM-bound Adam epilogue run under another CTA's main loop.
+template <bool A_KMAJOR, bool B_KMAJOR, int EPI, int NB, int OCC>
+__global__ void __launch_bounds__(TC_THREADS, OCC) tc_grouped_gemm_kernel(const TcParams p) {
   extern __shared__ __align__(1024) char tc_smem[];
   __shared__ __align__(8) unsigned long long bar_full[TC_MAX_STAGES];
   __shared__ __align__(8) unsigned long long bar_empty[TC_MAX_STAGES];
@@ -230,7 +234,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_grouped_gemm_kernel(const Tc
   char* smem = tc_smem + ((1024u - (smem_u32(tc_smem) & 1023u)) & 1023u);
 
   const int stride = tc_region_stride(bn);
-  const int n_main = tc_n_main(bn);
+  const int n_main = p.n_main;
+  const uint32_t tmem_cols = (uint32_t)p.tmem_cols;
   const int nkb = (p.K + TC_BK - 1) / TC_BK;
   const int nks = (p.K + 7) >> 3;  // k-steps of 8 that carry data
 
@@ -242,7 +247,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_grouped_gemm_kernel(const Tc
     mbar_init(smem_u32(&bar_done), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == TC_MMA_WARP) tmem_alloc(smem_u32(&tmem_slot), TC_TMEM_COLS);
+  if (warp == TC_MMA_WARP) tmem_alloc(smem_u32(&tmem_slot), tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -292,7 +297,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_grouped_gemm_kernel(const Tc
     const Rows RA = resolve(p.A, g);
     const Rows RB = resolve(p.B, g);
     const int npb = bn_pad >> 2;  // patches of the B tile (K-major tiles beyond bn are zero-filled)
-    constexpr int DEPTH = (NB == 4) ? 3 : 2;  // k-blocks of global loads in flight per thread
+    constexpr int DEPTH = (NB == 4 && OCC == 1) ? 3 : 2;  // k-blocks of global loads in flight per thread
     float4 ra[DEPTH][4], rb[DEPTH][NB];
     auto load_block = [&](int kb, float4 (&qa)[4], float4 (&qb)[NB]) {
       const int k0 = kb * TC_BK;
@@ -385,7 +390,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_grouped_gemm_kernel(const Tc
     };
     auto chunk_ok = [&](int c) { return c < nch && n0 + c * 16 < p.N; };  // warp-uniform
 
-    if (EPI == EPI_ADAM) {
+    if (EPI == EPI_ADAM && OCC == 2) {
+      // two CTAs per SM: the other CTA's main loop hides this one's memory latency; keep the registers low
+      for (int c = half; chunk_ok(c); c += 2) {
+        const int nb = n0 + c * 16;
+        float g[16];
+        tmem_chunk(c, g);
+        if (!m_ok) continue;
+        float w[16], mm[16], vv[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const long long off = (long long)(nb + j) * p.ldc + m;
+          const bool ok = nb + j < p.N;
+          w[j] = ok ? C[off] : 0.f;
+          mm[j] = ok ? Mo[off] : 0.f;
+          vv[j] = ok ? Vo[off] : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          if (nb + j < p.N) {
+            const long long off = (long long)(nb + j) * p.ldc + m;
+            adam_update(w[j], mm[j], vv[j], g[j], as);
+            C[off] = w[j]; Mo[off] = mm[j]; Vo[off] = vv[j];
+          }
+        }
+      }
+    } else if (EPI == EPI_ADAM) {
       // W / m / v of the NEXT chunk are requested before the current chunk is updated and stored, so the
       // ~48 loads per thread overlap the Adam arithmetic instead of serialising with it
       float w[2][16], mm[2][16], vv[2][16];
@@ -453,7 +483,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_grouped_gemm_kernel(const Tc
 
   tc_fence_before();
   __syncthreads();
-  if (warp == TC_MMA_WARP) tmem_dealloc(tmem_d, TC_TMEM_COLS);
+  if (warp == TC_MMA_WARP) tmem_dealloc(tmem_d, tmem_cols);
 }
 
 // N tile: the largest balanced tile (multiple of 16, <= 256) whose TMEM plan keeps every hi*hi region
@@ -478,18 +508,24 @@ static inline int tc_pick_stages(int bn) {
   return n > TC_MAX_STAGES ? TC_MAX_STAGES : (n < 2 ? 2 : n);
 }
 
-template <bool A_KMAJOR, bool B_KMAJOR, int EPI, int NB>
+static inline int tc_pow2_cols(int cols) {
+  int c = 32;
+  while (c < cols) c <<= 1;
+  return c;
+}
+
+template <bool A_KMAJOR, bool B_KMAJOR, int EPI, int NB, int OCC>
 static inline cudaError_t launch_tc_gemm_nb(const TcParams& p, int G, cudaStream_t stream) {
   static bool attr_set = false;  // per template instantiation
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tc_grouped_gemm_kernel<A_KMAJOR, B_KMAJOR, EPI, NB>,
+    cudaError_t e = cudaFuncSetAttribute(tc_grouped_gemm_kernel<A_KMAJOR, B_KMAJOR, EPI, NB, OCC>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BUDGET);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
   const size_t smem = (size_t)p.n_stages * tc_stage_bytes(p.bn) + 1024;
   dim3 grid((p.N + p.bn - 1) / p.bn, (p.M + TC_BM - 1) / TC_BM, G);
-  tc_grouped_gemm_kernel<A_KMAJOR, B_KMAJOR, EPI, NB><<<grid, TC_THREADS, smem, stream>>>(p);
+  tc_grouped_gemm_kernel<A_KMAJOR, B_KMAJOR, EPI, NB, OCC><<<grid, TC_THREADS, smem, stream>>>(p);
   count_launch();
   return cudaGetLastError();
 }
@@ -497,10 +533,23 @@ static inline cudaError_t launch_tc_gemm_nb(const TcParams& p, int G, cudaStream
 template <bool A_KMAJOR, bool B_KMAJOR, int EPI>
 static inline cudaError_t launch_tc_gemm(TcParams p, int G, cudaStream_t stream) {
   if (G <= 0 || p.M <= 0 || p.N <= 0) return cudaSuccess;
+  const int nks = (p.K + 7) / 8;
+  if ((EPI == EPI_ADAM || EPI == EPI_STORE) && !A_KMAJOR && !B_KMAJOR && nks <= TC_MAX_ACCUM) {
+    // short-K weight gradient: its epilogue (24 B per parameter for Adam) is the HBM-bound part of a round.
+    // 128-wide tiles, one stage (64 KB) and 256 TMEM columns -> two CTAs per SM overlap epilogue and main loop.
+    const int tiles = (p.N + 127) / 128;
+    p.bn = ((p.N + tiles - 1) / tiles + 15) / 16 * 16;
+    p.n_stages = 1;
+    p.n_main = 1;
+    p.tmem_cols = tc_pow2_cols(2 * tc_region_stride(p.bn));
+    return launch_tc_gemm_nb<A_KMAJOR, B_KMAJOR, EPI, 4, 2>(p, G, stream);
+  }
   p.bn = tc_pick_bn(p.N, p.K);
   p.n_stages = tc_pick_stages(p.bn);
-  if (p.bn <= 128) return launch_tc_gemm_nb<A_KMAJOR, B_KMAJOR, EPI, 4>(p, G, stream);
-  return launch_tc_gemm_nb<A_KMAJOR, B_KMAJOR, EPI, 8>(p, G, stream);
+  p.n_main = tc_n_main(p.bn);
+  p.tmem_cols = TC_TMEM_COLS;
+  if (p.bn <= 128) return launch_tc_gemm_nb<A_KMAJOR, B_KMAJOR, EPI, 4, 1>(p, G, stream);
+  return launch_tc_gemm_nb<A_KMAJOR, B_KMAJOR, EPI, 8, 1>(p, G, stream);
 }
 
 // The tensor-core path needs float4-addressable operands: 16-byte aligned bases / strides, the

@@ -201,6 +201,28 @@ int cgl_mix_allreduce(cgl_comm_t comm, int C_local, int64_t n, const float* w_lo
                       const int32_t* rows, const float* src, int64_t ld_src, float* out,
                       cgl_stream_t stream);
 
+/* ---- live kernel timing (bench.py's roofline) ---------------------------------------------------------
+ * cgl_profile_enable(1) makes every instrumented kernel class record a CUDA-event pair on its launching stream
+ * together with its ALGORITHMIC bytes and FLOPs; cgl_profile_summary(tag, ...) synchronises
+ * those events and returns the totals since the last cgl_profile_enable call. Off by default.            */
+#define CGL_PROF_FWD_TC 0
+#define CGL_PROF_BWD_TC 1
+#define CGL_PROF_WGRAD_ADAM_TC 2
+#define CGL_PROF_WGRAD_TC 3
+#define CGL_PROF_FWD_FFMA 4
+#define CGL_PROF_BWD_FFMA 5
+#define CGL_PROF_WGRAD_ADAM_FFMA 6
+#define CGL_PROF_WGRAD_FFMA 7
+#define CGL_PROF_HEAD 8
+#define CGL_PROF_BN_FWD 9
+#define CGL_PROF_BN_BWD 10
+#define CGL_PROF_MIX 11
+#define CGL_PROF_ELEMENTWISE 12
+#define CGL_PROF_NUM_TAGS 13
+int cgl_profile_enable(int on);
+const char* cgl_profile_tag_name(int tag);
+int cgl_profile_summary(int tag, double* out_ms, double* out_bytes, double* out_flops, long long* out_launches);
+
 /* ---- kernel selection (tests / profiling) ------------------------------------------------------
  * The Linear products run on one of two sm_100a kernels of this library, chosen by shape and alignment:
  * the tcgen05/TMEM 3xTF32 grouped GEMM (wide, 16-byte aligned layers) or the exact-fp32 FFMA grouped GEMM
