@@ -34,6 +34,7 @@ struct HeadParams {
   long long w_off, b_off;
   const int* step;
   float lr, b1, b2, eps;
+  const AdamScalars* scal;  // [G] (train)
   const int* n_valid0;  // [G] valid rows among the first rows0 (NULL: all)
   int loss_kind, last_act;
   float target0, target1;  // targets of rows [0,rows0) and [rows0,rows)
@@ -146,7 +147,7 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const HeadParams p) 
 
   // ---- Adam on the last layer: dW[j][h] = sum_r dlogit[r][j] * h[r][h]; db[j] = sum_r dlogit[r][j]
   if (p.train) {
-    const AdamScalars s = make_adam_scalars(p.step[rowid], p.lr, p.b1, p.b2, p.eps);
+    const AdamScalars s = p.scal ? p.scal[g] : make_adam_scalars(p.step[rowid], p.lr, p.b1, p.b2, p.eps);
     float* Mo = p.adam_m + (long long)rowid * p.ldp;
     float* Vo = p.adam_v + (long long)rowid * p.ldp;
     for (int h = tid; h < H; h += HEAD_THREADS) {
@@ -178,11 +179,6 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const HeadParams p) 
       Bv[tid] = w; Mo[o] = mm; Vo[o] = vv;
     }
   }
-}
-
-__global__ void bump_step_kernel(int G, int* step, const int* ids) {
-  int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g < G) step[ids ? ids[g] : g] += 1;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -224,6 +220,7 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 struct Workspace {
   float* H[CGL_MAX_LAYERS];   // H[i], i=1..L-1 : [G][rows][dims[i]]
   float* dZ[CGL_MAX_LAYERS];  // same shapes
+  AdamScalars* scal;          // [G]
 };
 static Workspace carve(const cgl_mlp_desc* a, int G, int rows, void* ws) {
   Workspace w;
@@ -233,12 +230,13 @@ static Workspace carve(const cgl_mlp_desc* a, int G, int rows, void* ws) {
     w.H[i] = (float*)p; p += bytes;
     w.dZ[i] = (float*)p; p += bytes;
   }
+  w.scal = (AdamScalars*)p;
   return w;
 }
 static size_t ws_bytes(const cgl_mlp_desc* a, int G, int rows) {
   size_t b = 0;
   for (int i = 1; i < a->n_layers; ++i) b += 2 * align_up((size_t)G * rows * a->dims[i] * sizeof(float), 256);
-  return b + 256;
+  return b + align_up((size_t)G * sizeof(AdamScalars), 256) + 256;
 }
 
 static int forward_hidden(const cgl_mlp_desc* a, const cgl_mlp_layout& lay, int G, int rows, const RowMap& X,
@@ -264,6 +262,7 @@ static int launch_head(const cgl_mlp_desc* a, const cgl_mlp_layout& lay, int G, 
   h.params = params; h.adam_m = am; h.adam_v = av; h.ldp = ldp; h.ids = ids;
   h.w_off = lay.w_off[L - 1]; h.b_off = lay.b_off[L - 1];
   h.step = step;
+  h.scal = train ? w.scal : nullptr;
   if (cfg) { h.lr = cfg->lr; h.b1 = cfg->beta1; h.b2 = cfg->beta2; h.eps = cfg->eps; }
   h.n_valid0 = n_valid0;
   h.loss_kind = loss_kind; h.last_act = a->act[L - 1];
@@ -317,7 +316,8 @@ extern "C" int cgl_d_step(const cgl_mlp_desc* arch, int G, float* params, float*
   const int L = arch->n_layers;
   const int d = arch->dims[0];
 
-  bump_step_kernel<<<(G + 127) / 128, 128, 0, st>>>(G, step, client_ids);
+  adam_prepare_kernel<<<(G + 127) / 128, 128, 0, st>>>(G, step, client_ids, cfg->lr, cfg->beta1, cfg->beta2, cfg->eps,
+                                                      w.scal);
   CGL_CHECK_LAUNCH();
 
   // rows [0,B): real[g], rows [B,2B): fake[fake_idx[g]]   (CGLGAN/2DMG/main.py:361-363)
@@ -336,7 +336,7 @@ extern "C" int cgl_d_step(const cgl_mlp_desc* arch, int G, float* params, float*
                                          arch->lrelu_slope, w.dZ[l], (long long)rows * in, st));
     }
     RowMap Xin = (l == 0) ? X : single_rows(w.H[l], (long long)rows * in, nullptr, in);
-    const AdamArgs ad = {adam_m, adam_v, step, cfg->lr, cfg->beta1, cfg->beta2, cfg->eps};
+    const AdamArgs ad = {adam_m, adam_v, step, cfg->lr, cfg->beta1, cfg->beta2, cfg->eps, w.scal};
     CGL_CHECK_CUDA(run_linear_wgrad(G, rows, in, out, w.dZ[l + 1], (long long)rows * out, Xin, params, ldp, client_ids,
                                     lay.w_off[l], lay.b_off[l], &ad, st));
   }
@@ -393,6 +393,13 @@ extern "C" int cgl_set_gemm_mode(int mode) {
   return CGL_OK;
 }
 extern "C" int cgl_get_gemm_mode(void) { return g_gemm_mode; }
+
+// Bring-up only: CTA (0,0,g) of every tcgen05 GEMM launched from this translation unit (cgl_d_step, cgl_g_loss,
+// cgl_linear_*) stamps clock64() at its milestones into buf[g*16 + i] (csrc/tc_gemm.cuh). NULL switches it off.
+extern "C" int cgl_debug_set_timeline(long long* device_buf) {
+  CGL_CHECK_CUDA(cudaMemcpyToSymbol(g_tc_timeline, &device_buf, sizeof(device_buf)));
+  return CGL_OK;
+}
 
 // ---- building blocks ------------------------------------------------------------------------
 extern "C" int cgl_linear_fwd(int G, int rows, int in, int out, const float* x, int64_t x_gstride, const float* wbase,

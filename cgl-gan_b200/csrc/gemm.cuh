@@ -185,6 +185,7 @@ struct GemmParams {
   float* adam_m;
   float* adam_v;
   const int* step;  // step[row(g)], already incremented for this update
+  const AdamScalars* scal;  // [G] precomputed scalars of this step (NULL: derive from step)
   float lr, b1, b2, eps;
   // EPI_STORE with bias gradient: db[m] = sum_k Aop[m][k] stored at cbase + ... + dbias_off (or -1)
   long long dbias_off;
@@ -318,7 +319,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) grouped_gemm_kernel(const GemmPa
       if (m < p.M) (p.cbase + (long long)rowid * p.c_gstride + p.dbias_off)[m] = bsum;
     }
   } else {  // EPI_ADAM
-    const AdamScalars s = make_adam_scalars(p.step[rowid], p.lr, p.b1, p.b2, p.eps);
+    const AdamScalars s = p.scal ? p.scal[g] : make_adam_scalars(p.step[rowid], p.lr, p.b1, p.b2, p.eps);
     float* Mo = p.adam_m + (long long)rowid * p.c_gstride + p.c_off;
     float* Vo = p.adam_v + (long long)rowid * p.c_gstride + p.c_off;
 #pragma unroll

@@ -86,6 +86,7 @@ struct BnBwdParams {
   const float* save_mean; const float* save_invstd;
   float* params; float* adam_m; float* adam_v; long long ldp; const int* ids; long long gamma_off, beta_off;
   const int* step; float lr, b1, b2, eps;
+  const AdamScalars* scal;
 };
 
 __global__ void __launch_bounds__(128) bn_bwd_kernel(const BnBwdParams p) {
@@ -125,7 +126,7 @@ __global__ void __launch_bounds__(128) bn_bwd_kernel(const BnBwdParams p) {
     const float d = dz[(long long)r * p.F];
     dz[(long long)r * p.F] = (d - mb - (u[(long long)r * p.F] - mean) * k) * a;
   }
-  const AdamScalars s = make_adam_scalars(p.step[rowid], p.lr, p.b1, p.b2, p.eps);
+  const AdamScalars s = p.scal ? p.scal[g] : make_adam_scalars(p.step[rowid], p.lr, p.b1, p.b2, p.eps);
   {
     float w = gamma, mm = p.adam_m[go], vv = p.adam_v[go];
     adam_update(w, mm, vv, dgamma, s);
@@ -154,11 +155,6 @@ __global__ void act_bwd_kernel(long long n, const float* __restrict__ dy, const 
   }
 }
 
-__global__ void bump_rows_step_kernel(int G, int* step, const int* ids) {
-  int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g < G) step[ids ? ids[g] : g] += 1;
-}
-
 // ---- workspace ----------------------------------------------------------------------------------
 static inline size_t up256(size_t x) { return (x + 255) / 256 * 256; }
 
@@ -168,6 +164,7 @@ struct MlpWs {
   float* mean[CGL_MAX_LAYERS];
   float* invstd[CGL_MAX_LAYERS];
   float* dZ[2];                   // backward ping-pong, G*rows*maxdim each
+  AdamScalars* scal;              // [G] scalars of the current Adam step
   size_t bytes;
 };
 static MlpWs mlp_carve(const cgl_mlp_desc* a, int G, int rows, void* base) {
@@ -185,6 +182,7 @@ static MlpWs mlp_carve(const cgl_mlp_desc* a, int G, int rows, void* base) {
     }
   }
   for (int i = 0; i < 2; ++i) { w.dZ[i] = (float*)(p + off); off += up256((size_t)G * rows * maxdim * 4); }
+  w.scal = (AdamScalars*)(p + off); off += up256((size_t)G * sizeof(AdamScalars));
   w.bytes = off + 256;
   return w;
 }
@@ -278,7 +276,7 @@ extern "C" int cgl_mlp_backward(const cgl_mlp_desc* arch, int G, float* params, 
   }
   cudaStream_t st = (cudaStream_t)stream;
   const int L = arch->n_layers;
-  bump_rows_step_kernel<<<(G + 127) / 128, 128, 0, st>>>(G, step, ids);
+  adam_prepare_kernel<<<(G + 127) / 128, 128, 0, st>>>(G, step, ids, cfg->lr, cfg->beta1, cfg->beta2, cfg->eps, w.scal);
   CGL_CHECK_LAUNCH();
 
   // gradient wrt the last layer's pre-activation
@@ -291,7 +289,7 @@ extern "C" int cgl_mlp_backward(const cgl_mlp_desc* arch, int G, float* params, 
                                                                        arch->lrelu_slope);
     CGL_CHECK_LAUNCH();
   }
-  const AdamArgs ad = {adam_m, adam_v, step, cfg->lr, cfg->beta1, cfg->beta2, cfg->eps};
+  const AdamArgs ad = {adam_m, adam_v, step, cfg->lr, cfg->beta1, cfg->beta2, cfg->eps, w.scal};
   for (int l = L - 1; l >= 0; --l) {
     const int in = arch->dims[l], out = arch->dims[l + 1];
     float* dU = w.dZ[cur];
@@ -303,7 +301,7 @@ extern "C" int cgl_mlp_backward(const cgl_mlp_desc* arch, int G, float* params, 
       b.save_mean = w.mean[l]; b.save_invstd = w.invstd[l];
       b.params = params; b.adam_m = adam_m; b.adam_v = adam_v; b.ldp = ldp; b.ids = ids;
       b.gamma_off = lay.bn_w_off[l]; b.beta_off = lay.bn_b_off[l];
-      b.step = step; b.lr = cfg->lr; b.b1 = cfg->beta1; b.b2 = cfg->beta2; b.eps = cfg->eps;
+      b.step = step; b.lr = cfg->lr; b.b1 = cfg->beta1; b.b2 = cfg->beta2; b.eps = cfg->eps; b.scal = w.scal;
       dim3 grid((out + 127) / 128, G);
       ProfScope prof(CGL_PROF_BN_BWD, 12.0 * G * rows * (double)out, 0.0, st);  // dz, u read, du written
       bn_bwd_kernel<<<grid, 128, 0, st>>>(b);

@@ -21,7 +21,7 @@ __global__ void __launch_bounds__(128) bias_grad_kernel(int rows, int out, const
                                                         long long dy_gstride, float* base, long long ld,
                                                         const int* ids, long long b_off, float* adam_m,
                                                         float* adam_v, const int* step, float lr, float b1, float b2,
-                                                        float eps) {
+                                                        float eps, const AdamScalars* scal) {
   const int g = blockIdx.y;
   const int o = blockIdx.x * blockDim.x + threadIdx.x;
   if (o >= out) return;
@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(128) bias_grad_kernel(int rows, int out, const
   const int rowid = ids ? ids[g] : g;
   const long long off = (long long)rowid * ld + b_off + o;
   if (ADAM) {
-    const AdamScalars s = make_adam_scalars(step[rowid], lr, b1, b2, eps);
+    const AdamScalars s = scal ? scal[g] : make_adam_scalars(step[rowid], lr, b1, b2, eps);
     float w = base[off], mm = adam_m[off], vv = adam_v[off];
     adam_update(w, mm, vv, gsum, s);
     base[off] = w; adam_m[off] = mm; adam_v[off] = vv;
@@ -107,7 +107,20 @@ static inline cudaError_t run_linear_bwd_data(int G, int rows, int in, int out, 
 
 struct AdamArgs {
   float* m; float* v; const int* step; float lr, b1, b2, eps;
+  const AdamScalars* scal;  // [G] per-group scalars from adam_prepare_kernel (NULL: derived in every kernel)
 };
+
+// step[row(g)] += 1 and the step's Adam scalars (bias corrections: two double-precision pow) computed ONCE per
+// group; every fused-Adam epilogue of the call then reads 7 floats instead of redoing fp64 math per thread.
+static __global__ void adam_prepare_kernel(int G, int* step, const int* ids, float lr, float b1, float b2, float eps,
+                                           AdamScalars* scal) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= G) return;
+  const int row = ids ? ids[g] : g;
+  const int t = step[row] + 1;
+  step[row] = t;
+  scal[g] = make_adam_scalars(t, lr, b1, b2, eps);
+}
 
 // dW[g][o][i] = sum_r dy[g][r][o] * x[g][r][i], db[g][o] = sum_r dy[g][r][o];
 // adam != NULL: applied in the epilogue as an Adam step on W / b (base = params);
@@ -127,9 +140,11 @@ static inline cudaError_t run_linear_wgrad(int G, int rows, int in, int out, con
     p.A = X;   // MN-major: line = r, contiguous along i
     p.B = DY;  // MN-major: line = r, contiguous along o
     p.cbase = base; p.c_gstride = ld; p.cidx = ids; p.c_off = w_off; p.ldc = in;
+    p.c_vec = (aligned16(base) && ld % 4 == 0 && w_off % 4 == 0 && in % 4 == 0 &&
+               (!adam || (aligned16(adam->m) && aligned16(adam->v)))) ? 1 : 0;
     cudaError_t e;
     if (adam) {
-      p.adam_m = adam->m; p.adam_v = adam->v; p.step = adam->step;
+      p.adam_m = adam->m; p.adam_v = adam->v; p.step = adam->step; p.scal = adam->scal;
       p.lr = adam->lr; p.b1 = adam->b1; p.b2 = adam->b2; p.eps = adam->eps;
       e = launch_tc_gemm<false, false, EPI_ADAM>(p, G, st);
     } else {
@@ -139,10 +154,10 @@ static inline cudaError_t run_linear_wgrad(int G, int rows, int in, int out, con
     dim3 grid((out + 127) / 128, G);
     if (adam) {
       bias_grad_kernel<true><<<grid, 128, 0, st>>>(rows, out, dy, dy_gstride, base, ld, ids, b_off, adam->m, adam->v,
-                                                   adam->step, adam->lr, adam->b1, adam->b2, adam->eps);
+                                                   adam->step, adam->lr, adam->b1, adam->b2, adam->eps, adam->scal);
     } else {
       bias_grad_kernel<false><<<grid, 128, 0, st>>>(rows, out, dy, dy_gstride, base, ld, ids, b_off, nullptr, nullptr,
-                                                    nullptr, 0.f, 0.f, 0.f, 0.f);
+                                                    nullptr, 0.f, 0.f, 0.f, 0.f, nullptr);
     }
     count_launch();
     return cudaGetLastError();
@@ -150,7 +165,7 @@ static inline cudaError_t run_linear_wgrad(int G, int rows, int in, int out, con
   GemmParams p = wgrad_params(rows, in, out, dy, dy_gstride, X, base, ld, ids, w_off, b_off);
   if (b_off < 0) { p.bias_off = -1; p.dbias_off = -1; }
   if (adam) {
-    p.adam_m = adam->m; p.adam_v = adam->v; p.step = adam->step;
+    p.adam_m = adam->m; p.adam_v = adam->v; p.step = adam->step; p.scal = adam->scal;
     p.lr = adam->lr; p.b1 = adam->b1; p.b2 = adam->b2; p.eps = adam->eps;
     return launch_grouped_gemm<false, false, EPI_ADAM>(p, G, st);
   }

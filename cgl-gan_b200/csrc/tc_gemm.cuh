@@ -175,6 +175,15 @@ __device__ __forceinline__ void tc_split_store(char* hi, char* lo, uint32_t off,
   *reinterpret_cast<float4*>(lo + off) = l;
 }
 
+// Bring-up instrumentation: when cgl_debug_set_timeline() installs a buffer, CTA (0,0,g) writes clock64() stamps
+// of its milestones to timeline[g*16 + i] (i: 0 entry, 1 setup done, 2 first loads issued, 3 first stage
+// stored, 4 last stage stored, 5 accumulator complete, 6 epilogue done, 7 exit; 8 MMA first full, 9 MMA last commit).
+__device__ long long* g_tc_timeline = nullptr;
+#define TC_STAMP(i)                                                                      \
+  do {                                                                                   \
+    if (g_tc_timeline && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0) g_tc_timeline[blockIdx.z * 16 + (i)] = clock64(); \
+  } while (0)
+
 // EPI_* as in gemm.cuh. Output element (m, n) lives at C + n*ldc + m.
 struct TcParams {
   int M, N, K;
@@ -184,10 +193,12 @@ struct TcParams {
   int tmem_cols;  // TMEM columns to allocate: power of two >= (n_main + 1) * round_up(bn, 32)
   RowMap A, B;
   float* cbase; long long c_gstride; const int* cidx; long long c_off; int ldc;
+  int c_vec;  // host-verified: every output row start (and adam_m / adam_v) is 16-byte aligned, ldc % 4 == 0
   const float* bias_base; long long bias_gstride; const int* bias_idx; long long bias_off;  // bias[m] (EPI_FWD)
   int act; float slope;
   const float* saved; long long saved_gstride;  // EPI_BWD_DATA: saved[g] + n*ldc + m
   float* adam_m; float* adam_v; const int* step; float lr, b1, b2, eps;  // EPI_ADAM
+  const AdamScalars* scal;  // EPI_ADAM: [G] precomputed scalars of this step (NULL: derive from step)
 };
 
 // TMEM plan (512 columns, 1 CTA per SM). The tensor core TRUNCATES when it adds into an fp32
@@ -224,6 +235,7 @@ __global__ void __launch_bounds__(TC_THREADS, OCC) tc_grouped_gemm_kernel(const 
   const int n0 = blockIdx.x * p.bn;
   const int bn = p.bn;
   const int nst = p.n_stages;
+  if (warp == 0) TC_STAMP(0);
 
   // stage layout: [A hi | A lo | B hi | B lo]
   const uint32_t a_bytes = TC_BM * TC_BK * 4;
@@ -252,6 +264,7 @@ __global__ void __launch_bounds__(TC_THREADS, OCC) tc_grouped_gemm_kernel(const 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = tmem_slot;
+  if (warp == 0) TC_STAMP(1);
 
   if (warp == TC_MMA_WARP) {
     // ===== MMA issuer: one thread =====
@@ -268,6 +281,7 @@ __global__ void __launch_bounds__(TC_THREADS, OCC) tc_grouped_gemm_kernel(const 
       uint32_t par = 0;
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(smem_u32(&bar_full[s]), par);
+        if (kb == 0) TC_STAMP(8);
         tc_fence_after();
         const uint32_t sa_hi = smem_u32(smem + (size_t)s * stage_bytes);
         const uint32_t sa_lo = sa_hi + a_bytes, sb_hi = sa_hi + 2 * a_bytes, sb_lo = sb_hi + b_bytes;
@@ -290,10 +304,25 @@ __global__ void __launch_bounds__(TC_THREADS, OCC) tc_grouped_gemm_kernel(const 
         if (++s == nst) { s = 0; par ^= 1u; }
       }
       umma_commit(smem_u32(&bar_done));
+      TC_STAMP(9);
     }
     __syncwarp();
   } else {
-    // ===== loader warps: global -> registers (two k-blocks in flight) -> split -> shared =====
+    // epilogue operands that do not depend on the accumulator are requested now, under the main loop
+    const int q = warp & 3;        // TMEM lane quarter this warp may read
+    const int half = warp >> 2;    // warps w and w+4 share a quarter and alternate 16-column chunks
+    const int m = m0 + q * 32 + lane;
+    const bool m_ok = m < p.M;
+    const int rowid = p.cidx ? p.cidx[g] : g;
+    float bias = 0.f;
+    if (EPI == EPI_FWD && p.bias_base && m_ok) {
+      const int brow = p.bias_idx ? p.bias_idx[g] : g;
+      bias = __ldg(p.bias_base + (long long)brow * p.bias_gstride + p.bias_off + m);
+    }
+    AdamScalars as = {};
+    if (EPI == EPI_ADAM) as = p.scal ? p.scal[g] : make_adam_scalars(p.step[rowid], p.lr, p.b1, p.b2, p.eps);
+
+    // ===== loader warps: global -> registers (several k-blocks in flight) -> split -> shared =====
     const Rows RA = resolve(p.A, g);
     const Rows RB = resolve(p.B, g);
     const int npb = bn_pad >> 2;  // patches of the B tile (K-major tiles beyond bn are zero-filled)
@@ -335,39 +364,31 @@ __global__ void __launch_bounds__(TC_THREADS, OCC) tc_grouped_gemm_kernel(const 
 #pragma unroll
     for (int d = 0; d < DEPTH; ++d)
       if (d < nkb) load_block(d, ra[d], rb[d]);
+    if (warp == 0) TC_STAMP(2);
     for (int kb0 = 0; kb0 < nkb; kb0 += DEPTH) {
 #pragma unroll
       for (int d = 0; d < DEPTH; ++d) {
         const int kb = kb0 + d;
         if (kb < nkb) {
           store_block(ra[d], rb[d]);
+          if (kb == 0 && warp == 0) TC_STAMP(3);
           if (kb + DEPTH < nkb) load_block(kb + DEPTH, ra[d], rb[d]);
         }
       }
     }
+    if (warp == 0) TC_STAMP(4);
 
     // ===== epilogue: TMEM -> registers -> fused op -> global =====
     mbar_wait(smem_u32(&bar_done), 0);
     tc_fence_after();
+    if (warp == 0) TC_STAMP(5);
 
-    const int q = warp & 3;        // TMEM lane quarter this warp may read
-    const int half = warp >> 2;    // warps w and w+4 share a quarter and alternate 16-column chunks
-    const int m = m0 + q * 32 + lane;
-    const bool m_ok = m < p.M;
-    const int rowid = p.cidx ? p.cidx[g] : g;
     float* C = p.cbase + (long long)rowid * p.c_gstride + p.c_off;
     const int n_used = nks < n_main ? nks : n_main;
 
-    float bias = 0.f;
-    if (EPI == EPI_FWD && p.bias_base && m_ok) {
-      const int brow = p.bias_idx ? p.bias_idx[g] : g;
-      bias = __ldg(p.bias_base + (long long)brow * p.bias_gstride + p.bias_off + m);
-    }
-    AdamScalars as = {};
     float* Mo = nullptr;
     float* Vo = nullptr;
     if (EPI == EPI_ADAM) {
-      as = make_adam_scalars(p.step[rowid], p.lr, p.b1, p.b2, p.eps);
       Mo = p.adam_m + (long long)rowid * p.c_gstride + p.c_off;
       Vo = p.adam_v + (long long)rowid * p.c_gstride + p.c_off;
     }
@@ -390,8 +411,56 @@ __global__ void __launch_bounds__(TC_THREADS, OCC) tc_grouped_gemm_kernel(const 
     };
     auto chunk_ok = [&](int c) { return c < nch && n0 + c * 16 < p.N; };  // warp-uniform
 
-    if (EPI == EPI_ADAM && OCC == 2) {
-      // two CTAs per SM: the other CTA's main loop hides this one's memory latency; keep the registers low
+    if (EPI == EPI_ADAM && p.c_vec) {
+      // Adam is the HBM-bound part of a round (24 B per parameter). The accumulator tile goes TMEM -> shared
+      // ([n][m], m contiguous like W) through the operand stages, which are idle now; then all 256 threads
+      // stream W / m / v as float4 along m: 512 contiguous bytes per warp request and UNR*3 independent 16-byte
+      // loads in flight per thread, instead of 4-byte accesses that leave the memory pipeline mostly empty.
+      float* T = reinterpret_cast<float*>(smem);
+      for (int c = half; chunk_ok(c); c += 2) {
+        float gv[16];
+        tmem_chunk(c, gv);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) T[(c * 16 + j) * TC_BM + q * 32 + lane] = gv[j];
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(TC_LOADER_THREADS) : "memory");  // the 8 loader / epilogue warps only
+      const int n_valid = (p.N - n0 < bn) ? (p.N - n0) : bn;
+      const int m4_valid = ((p.M - m0 < TC_BM) ? (p.M - m0) : TC_BM) >> 2;   // M % 4 == 0 (MN-major A operand)
+      const int items = n_valid * (TC_BM / 4);
+      constexpr int UNR = (OCC == 2) ? 3 : 4;
+      for (int i0 = tid; i0 < items; i0 += TC_LOADER_THREADS * UNR) {
+        float4 w4[UNR], a4[UNR], v4[UNR];
+        long long off[UNR];
+        bool ok[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+          const int i = i0 + u * TC_LOADER_THREADS;
+          const int n = i >> 5, mq = i & 31;
+          ok[u] = i < items && mq < m4_valid;
+          off[u] = (long long)(n0 + n) * p.ldc + m0 + mq * 4;
+          if (ok[u]) {
+            w4[u] = *reinterpret_cast<const float4*>(C + off[u]);
+            a4[u] = *reinterpret_cast<const float4*>(Mo + off[u]);
+            v4[u] = *reinterpret_cast<const float4*>(Vo + off[u]);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+          if (ok[u]) {
+            const int i = i0 + u * TC_LOADER_THREADS;
+            const float4 g4 = *reinterpret_cast<const float4*>(T + (i >> 5) * TC_BM + (i & 31) * 4);
+            adam_update(w4[u].x, a4[u].x, v4[u].x, g4.x, as);
+            adam_update(w4[u].y, a4[u].y, v4[u].y, g4.y, as);
+            adam_update(w4[u].z, a4[u].z, v4[u].z, g4.z, as);
+            adam_update(w4[u].w, a4[u].w, v4[u].w, g4.w, as);
+            *reinterpret_cast<float4*>(C + off[u]) = w4[u];
+            *reinterpret_cast<float4*>(Mo + off[u]) = a4[u];
+            *reinterpret_cast<float4*>(Vo + off[u]) = v4[u];
+          }
+        }
+      }
+    } else if (EPI == EPI_ADAM) {
+      // unaligned packed rows: scalar accesses, one TMEM chunk at a time
       for (int c = half; chunk_ok(c); c += 2) {
         const int nb = n0 + c * 16;
         float g[16];
@@ -414,43 +483,6 @@ __global__ void __launch_bounds__(TC_THREADS, OCC) tc_grouped_gemm_kernel(const 
             C[off] = w[j]; Mo[off] = mm[j]; Vo[off] = vv[j];
           }
         }
-      }
-    } else if (EPI == EPI_ADAM) {
-      // W / m / v of the NEXT chunk are requested before the current chunk is updated and stored, so the
-      // ~48 loads per thread overlap the Adam arithmetic instead of serialising with it
-      float w[2][16], mm[2][16], vv[2][16];
-      auto fetch = [&](int c, float (&fw)[16], float (&fm)[16], float (&fv)[16]) {
-        const int nb = n0 + c * 16;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const long long off = (long long)(nb + j) * p.ldc + m;
-          const bool ok = m_ok && nb + j < p.N;
-          fw[j] = ok ? C[off] : 0.f;
-          fm[j] = ok ? Mo[off] : 0.f;
-          fv[j] = ok ? Vo[off] : 0.f;
-        }
-      };
-      auto update = [&](int c, float (&fw)[16], float (&fm)[16], float (&fv)[16], const float (&g)[16]) {
-        const int nb = n0 + c * 16;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          if (m_ok && nb + j < p.N) {
-            const long long off = (long long)(nb + j) * p.ldc + m;
-            adam_update(fw[j], fm[j], fv[j], g[j], as);
-            C[off] = fw[j]; Mo[off] = fm[j]; Vo[off] = fv[j];
-          }
-        }
-      };
-      if (chunk_ok(half)) fetch(half, w[0], mm[0], vv[0]);
-      for (int c = half; chunk_ok(c); c += 4) {
-        float g[16];
-        tmem_chunk(c, g);
-        if (chunk_ok(c + 2)) fetch(c + 2, w[1], mm[1], vv[1]);
-        update(c, w[0], mm[0], vv[0], g);
-        if (!chunk_ok(c + 2)) break;
-        tmem_chunk(c + 2, g);
-        if (chunk_ok(c + 4)) fetch(c + 4, w[0], mm[0], vv[0]);
-        update(c + 2, w[1], mm[1], vv[1], g);
       }
     } else {
       for (int c = half; chunk_ok(c); c += 2) {
@@ -481,9 +513,11 @@ __global__ void __launch_bounds__(TC_THREADS, OCC) tc_grouped_gemm_kernel(const 
     }
   }
 
+  if (warp == 0) TC_STAMP(6);
   tc_fence_before();
   __syncthreads();
   if (warp == TC_MMA_WARP) tmem_dealloc(tmem_d, tmem_cols);
+  if (warp == 0) TC_STAMP(7);
 }
 
 // N tile: the largest balanced tile (multiple of 16, <= 256) whose TMEM plan keeps every hi*hi region

@@ -233,6 +233,8 @@ int cgl_profile_summary(int tag, double* out_ms, double* out_bytes, double* out_
 #define CGL_GEMM_TC 2
 int cgl_set_gemm_mode(int mode);
 int cgl_get_gemm_mode(void);
+/* Bring-up only: per-CTA clock64() milestones of the tcgen05 GEMM (csrc/tc_gemm.cuh); NULL switches it off. */
+int cgl_debug_set_timeline(long long* device_buf);
 
 /* ---- building blocks (exported for tests and for the host-side generator step) -------------
  * Grouped Linear over G independent groups, fp32:
