@@ -396,8 +396,10 @@ extern "C" int cgl_get_gemm_mode(void) { return g_gemm_mode; }
 
 // Bring-up only: CTA (0,0,g) of every tcgen05 GEMM launched from this translation unit (cgl_d_step, cgl_g_loss,
 // cgl_linear_*) stamps clock64() at its milestones into buf[g*16 + i] (csrc/tc_gemm.cuh). NULL switches it off.
+namespace cgl { cudaError_t set_timeline_gstep(long long* device_buf); }  // the other module's copy of the symbol
 extern "C" int cgl_debug_set_timeline(long long* device_buf) {
   CGL_CHECK_CUDA(cudaMemcpyToSymbol(g_tc_timeline, &device_buf, sizeof(device_buf)));
+  CGL_CHECK_CUDA(set_timeline_gstep(device_buf));
   return CGL_OK;
 }
 

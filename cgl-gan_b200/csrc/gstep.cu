@@ -194,6 +194,10 @@ static int validate_mlp(const cgl_mlp_desc* a) {
   return CGL_OK;
 }
 
+cudaError_t set_timeline_gstep(long long* device_buf) {
+  return cudaMemcpyToSymbol(g_tc_timeline, &device_buf, sizeof(device_buf));
+}
+
 }  // namespace cgl
 
 using namespace cgl;

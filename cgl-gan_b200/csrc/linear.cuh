@@ -70,6 +70,8 @@ static inline cudaError_t run_linear_fwd(int G, int rows, int in, int out, const
     p.M = out; p.N = rows; p.K = in;
     p.A = W; p.B = X;
     p.cbase = y; p.c_gstride = y_gstride; p.cidx = nullptr; p.c_off = 0; p.ldc = out;
+    p.c_vec = (aligned16(y) && y_gstride % 4 == 0 && out % 4 == 0 &&
+               (b_off < 0 || (aligned16(params) && ldp % 4 == 0 && b_off % 4 == 0))) ? 1 : 0;
     p.bias_base = (b_off >= 0) ? params : nullptr; p.bias_gstride = ldp; p.bias_idx = ids; p.bias_off = b_off;
     p.act = act; p.slope = slope;
     return launch_tc_gemm<true, true, EPI_FWD>(p, G, st);
@@ -95,6 +97,8 @@ static inline cudaError_t run_linear_bwd_data(int G, int rows, int in, int out, 
     p.A = W;   // MN-major: line = o (contraction), contiguous along i
     p.B = DY;  // K-major : line = r, contiguous along o
     p.cbase = dx; p.c_gstride = dx_gstride; p.cidx = nullptr; p.c_off = 0; p.ldc = in;
+    p.c_vec = (aligned16(dx) && dx_gstride % 4 == 0 && in % 4 == 0 &&
+               (!saved || (aligned16(saved) && saved_gstride % 4 == 0))) ? 1 : 0;
     p.saved = saved; p.saved_gstride = saved_gstride; p.act = act; p.slope = slope;
     if (saved) return launch_tc_gemm<false, true, EPI_BWD_DATA>(p, G, st);
     return launch_tc_gemm<false, true, EPI_STORE>(p, G, st);

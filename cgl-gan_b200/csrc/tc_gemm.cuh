@@ -89,6 +89,15 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 // 32 lanes x 16 consecutive fp32 columns: thread i of the warp gets lane (base + i)
+__device__ __forceinline__ void tmem_ld16_async(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   uint32_t r[16];
   asm volatile(
@@ -398,16 +407,36 @@ __global__ void __launch_bounds__(TC_THREADS, OCC) tc_grouped_gemm_kernel(const 
     // accumulator chunk: 16 columns of this thread's lane, summed over the TMEM regions
     auto tmem_chunk = [&](int c, float (&v)[16]) {
       const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 16);
+      if (OCC == 2) {  // register-lean variant: always exactly one main region plus the corrections
+        float t[16];
+        tmem_ld16(taddr + (uint32_t)stride, v);
+        tmem_ld16(taddr, t);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] += t[j];
+        return;
+      }
+      // up to four regions are requested before one wait (the usual plans have 2 or 4 regions)
+      uint32_t r0[16], r1[16], r2[16], r3[16];
+      tmem_ld16_async(taddr + (uint32_t)stride, r0);                    // main region 1
+      tmem_ld16_async(taddr, r1);                                       // corrections
+      if (n_used >= 2) tmem_ld16_async(taddr + (uint32_t)(2 * stride), r2);
+      if (n_used >= 3) tmem_ld16_async(taddr + (uint32_t)(3 * stride), r3);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float a = __uint_as_float(r0[j]);
+        if (n_used >= 2) a += __uint_as_float(r2[j]);
+        if (n_used >= 3) a += __uint_as_float(r3[j]);
+        v[j] = a;
+      }
       float t[16];
-      tmem_ld16(taddr + (uint32_t)stride, v);  // main regions first, the small correction last
-      for (int r = 2; r <= n_used; ++r) {
+      for (int r = 4; r <= n_used; ++r) {
         tmem_ld16(taddr + (uint32_t)(r * stride), t);
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] += t[j];
       }
-      tmem_ld16(taddr, t);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] += t[j];
+      for (int j = 0; j < 16; ++j) v[j] += __uint_as_float(r1[j]);      // the small correction last
     };
     auto chunk_ok = [&](int c) { return c < nch && n0 + c * 16 < p.N; };  // warp-uniform
 
@@ -481,6 +510,54 @@ __global__ void __launch_bounds__(TC_THREADS, OCC) tc_grouped_gemm_kernel(const 
             const long long off = (long long)(nb + j) * p.ldc + m;
             adam_update(w[j], mm[j], vv[j], g[j], as);
             C[off] = w[j]; Mo[off] = mm[j]; Vo[off] = vv[j];
+          }
+        }
+      }
+    } else if (EPI != EPI_ADAM && p.c_vec) {
+      // same route for the other epilogues: accumulators to shared ([n][m]), then float4 rows of the output
+      // (512 contiguous bytes per warp store; bias / saved activations as float4 too)
+      float* T = reinterpret_cast<float*>(smem);
+      for (int c = half; chunk_ok(c); c += 2) {
+        float gv[16];
+        tmem_chunk(c, gv);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) T[(c * 16 + j) * TC_BM + q * 32 + lane] = gv[j];
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(TC_LOADER_THREADS) : "memory");
+      const int n_valid = (p.N - n0 < bn) ? (p.N - n0) : bn;
+      const int m4_valid = ((p.M - m0 < TC_BM) ? (p.M - m0) : TC_BM) >> 2;   // M % 4 == 0 with c_vec
+      const int items = n_valid * (TC_BM / 4);
+      const int mq = tid & 31;                       // this thread's float4 column of the tile: fixed over the loop
+      float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (EPI == EPI_FWD && p.bias_base && mq < m4_valid) {
+        const int brow = p.bias_idx ? p.bias_idx[g] : g;
+        b4 = __ldg(reinterpret_cast<const float4*>(p.bias_base + (long long)brow * p.bias_gstride + p.bias_off + m0 + mq * 4));
+      }
+      constexpr int UNR = 4;
+      for (int i0 = tid; i0 < items; i0 += TC_LOADER_THREADS * UNR) {
+        float4 s4[UNR];
+        if (EPI == EPI_BWD_DATA && S) {
+#pragma unroll
+          for (int u = 0; u < UNR; ++u) {
+            const int i = i0 + u * TC_LOADER_THREADS;
+            if (i < items && mq < m4_valid)
+              s4[u] = __ldg(reinterpret_cast<const float4*>(S + (long long)(n0 + (i >> 5)) * p.ldc + m0 + mq * 4));
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+          const int i = i0 + u * TC_LOADER_THREADS;
+          if (i < items && mq < m4_valid) {
+            float4 o = *reinterpret_cast<const float4*>(T + (i >> 5) * TC_BM + mq * 4);
+            if (EPI == EPI_FWD) {
+              o.x = act_fwd(o.x + b4.x, p.act, p.slope); o.y = act_fwd(o.y + b4.y, p.act, p.slope);
+              o.z = act_fwd(o.z + b4.z, p.act, p.slope); o.w = act_fwd(o.w + b4.w, p.act, p.slope);
+            }
+            if (EPI == EPI_BWD_DATA && S) {
+              o.x *= act_bwd_from_out(s4[u].x, p.act, p.slope); o.y *= act_bwd_from_out(s4[u].y, p.act, p.slope);
+              o.z *= act_bwd_from_out(s4[u].z, p.act, p.slope); o.w *= act_bwd_from_out(s4[u].w, p.act, p.slope);
+            }
+            *reinterpret_cast<float4*>(C + (long long)(n0 + (i >> 5)) * p.ldc + m0 + mq * 4) = o;
           }
         }
       }

@@ -16,7 +16,7 @@ kind = sys.argv[4] if len(sys.argv) > 4 else "fwd"
 abi.require_device()
 abi.check(abi.lib.cgl_set_gemm_mode(2))
 st = lambda: C.c_void_p(torch.cuda.current_stream().cuda_stream)
-G = 148 * 8
+G = int(sys.argv[5]) if len(sys.argv) > 5 else 148 * 8
 ldp = (K * out + out + 31) // 32 * 32
 prm = torch.randn(G, ldp, device="cuda") * 0.05
 x = torch.randn(G, rows, K, device="cuda")
