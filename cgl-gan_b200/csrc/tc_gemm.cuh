@@ -218,7 +218,7 @@ struct TcParams {
 //   regions 1..n_main   : hi*hi, k-step ks goes to region 1 + ks % n_main
 // and the epilogue adds the regions in fp32 with round-to-nearest. The host picks bn so that no region
 // takes more than TC_MAX_ACCUM accumulations (tc_pick_bn).
-constexpr int TC_MAX_ACCUM = 36;
+constexpr int TC_MAX_ACCUM = 43;  // K = 1024 -> 128 k-steps over 3 regions (one 112-wide tile for a batch of 100)
 constexpr int TC_TMEM_COLS = 512;
 constexpr int TC_MAX_MAIN = 7;
 __host__ __device__ inline int tc_region_stride(int bn) { return (bn + 31) & ~31; }
