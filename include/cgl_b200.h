@@ -253,6 +253,14 @@ int cgl_linear_wgrad(int G, int rows, int in, int out, const float* dy, int64_t 
                      const float* x, int64_t x_gstride, float* gbase, int64_t ldg,
                      const int32_t* ids, int64_t w_off, int64_t b_off, cgl_stream_t stream);
 
+/* Weight gradient with the Adam step fused into the epilogue (what cgl_d_step / cgl_mlp_backward run per layer):
+ *   W[g] <- Adam(W[g], dy[g]^T x[g]),  b[g] <- Adam(b[g], colsum(dy[g]))   with torch.optim.Adam semantics (a7).
+ * step[row(g)] must already hold the step count INCLUDING this update (the bias corrections use it).            */
+int cgl_linear_wgrad_adam(int G, int rows, int in, int out, const float* dy, int64_t dy_gstride, const float* x,
+                          int64_t x_gstride, float* params, float* adam_m, float* adam_v, int64_t ld,
+                          const int32_t* step, const int32_t* ids, int64_t w_off, int64_t b_off, float lr, float beta1,
+                          float beta2, float eps, cgl_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

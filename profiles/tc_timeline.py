@@ -23,15 +23,21 @@ x = torch.randn(G, rows, K, device="cuda")
 y = torch.empty(G, rows, out, device="cuda")
 dy = torch.randn(G, rows, out, device="cuda")
 grad = torch.zeros(G, ldp, device="cuda")
+am, av = torch.zeros(G, ldp, device="cuda"), torch.zeros(G, ldp, device="cuda")
+step = torch.ones(G, dtype=torch.int32, device="cuda")
 
 
 def run():
     if kind == "fwd":
         abi.check(abi.lib.cgl_linear_fwd(G, rows, K, out, abi.ptr(x), rows * K, abi.ptr(prm), ldp, None, 0, K * out,
                                          abi.ACT_LRELU, 0.2, abi.ptr(y), rows * out, st()))
-    else:
+    elif kind == "wgrad":
         abi.check(abi.lib.cgl_linear_wgrad(G, rows, K, out, abi.ptr(dy), rows * out, abi.ptr(x), rows * K, abi.ptr(grad),
                                            ldp, None, 0, K * out, st()))
+    else:   # "adam": the fused weight-gradient + Adam epilogue
+        abi.check(abi.lib.cgl_linear_wgrad_adam(G, rows, K, out, abi.ptr(dy), rows * out, abi.ptr(x), rows * K,
+                                                abi.ptr(prm), abi.ptr(am), abi.ptr(av), ldp, abi.ptr(step), None, 0,
+                                                K * out, 2e-4, 0.5, 0.999, 1e-8, st()))
 
 
 run()
@@ -46,7 +52,7 @@ names = ["entry", "setup done", "loads issued", "stage0 stored", "all stored", "
          "mma first full", "mma last commit"]
 base = t[:, 0:1]
 rel = (t[:, :10] - base) / 1.92e3     # us at ~1.92 GHz
-for first in (slice(0, 148), slice(148 * 4, 148 * 5)):
+for first in (slice(0, min(148, G)), slice(G // 2, min(G // 2 + 148, G))):
     r = rel[first]
     print("CTAs", first.start, "..", first.stop, " (median us since entry)")
     for i, n in enumerate(names):
