@@ -478,10 +478,10 @@ __global__ void __launch_bounds__(TC_THREADS, OCC) tc_grouped_gemm_kernel(const 
           if (ok[u]) {
             const int i = i0 + u * TC_LOADER_THREADS;
             const float4 g4 = *reinterpret_cast<const float4*>(T + (i >> 5) * TC_BM + (i & 31) * 4);
-            adam_update(w4[u].x, a4[u].x, v4[u].x, g4.x, as);
-            adam_update(w4[u].y, a4[u].y, v4[u].y, g4.y, as);
-            adam_update(w4[u].z, a4[u].z, v4[u].z, g4.z, as);
-            adam_update(w4[u].w, a4[u].w, v4[u].w, g4.w, as);
+            adam_update_fast(w4[u].x, a4[u].x, v4[u].x, g4.x, as);
+            adam_update_fast(w4[u].y, a4[u].y, v4[u].y, g4.y, as);
+            adam_update_fast(w4[u].z, a4[u].z, v4[u].z, g4.z, as);
+            adam_update_fast(w4[u].w, a4[u].w, v4[u].w, g4.w, as);
             *reinterpret_cast<float4*>(C + off[u]) = w4[u];
             *reinterpret_cast<float4*>(Mo + off[u]) = a4[u];
             *reinterpret_cast<float4*>(Vo + off[u]) = v4[u];
@@ -508,7 +508,7 @@ __global__ void __launch_bounds__(TC_THREADS, OCC) tc_grouped_gemm_kernel(const 
         for (int j = 0; j < 16; ++j) {
           if (nb + j < p.N) {
             const long long off = (long long)(nb + j) * p.ldc + m;
-            adam_update(w[j], mm[j], vv[j], g[j], as);
+            adam_update_fast(w[j], mm[j], vv[j], g[j], as);
             C[off] = w[j]; Mo[off] = mm[j]; Vo[off] = vv[j];
           }
         }
