@@ -80,7 +80,7 @@ lib.cgl_profile_tag_name.restype = C.c_char_p
 lib.cgl_profile_summary.argtypes = [_i32, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                     C.POINTER(C.c_longlong)]
 lib.cgl_linear_wgrad_adam.argtypes = [_i32, _i32, _i32, _i32, _p, _i64, _p, _i64, _p, _p, _p, _i64, _p, _p, _i64, _i64,
-                                      _f32, _f32, _f32, _f32, _p]
+                                      _f32, _f32, _f32, _f32, _p, _p]
 lib.cgl_set_gemm_mode.argtypes = [_i32]
 lib.cgl_debug_set_timeline.argtypes = [_p]
 lib.cgl_get_gemm_mode.restype = C.c_int

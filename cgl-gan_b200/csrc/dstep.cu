@@ -440,12 +440,18 @@ extern "C" int cgl_linear_wgrad(int G, int rows, int in, int out, const float* d
 extern "C" int cgl_linear_wgrad_adam(int G, int rows, int in, int out, const float* dy, int64_t dy_gstride, const float* x,
                                      int64_t x_gstride, float* params, float* adam_m, float* adam_v, int64_t ld,
                                      const int32_t* step, const int32_t* ids, int64_t w_off, int64_t b_off, float lr,
-                                     float beta1, float beta2, float eps, cgl_stream_t stream) {
+                                     float beta1, float beta2, float eps, void* adam_scratch, cgl_stream_t stream) {
   CGL_REQUIRE(G >= 0 && G <= 65535 && rows > 0 && in > 0 && out > 0, "bad shape");
   CGL_REQUIRE(dy && x && params && adam_m && adam_v && step, "NULL tensor pointer");
   CGL_REQUIRE(b_off >= 0, "the fused Adam epilogue updates weight and bias together");
   RowMap X = single_rows(x, x_gstride, nullptr, in);
-  const AdamArgs ad = {adam_m, adam_v, step, lr, beta1, beta2, eps, nullptr};
+  AdamArgs ad = {adam_m, adam_v, step, lr, beta1, beta2, eps, nullptr};
+  if (adam_scratch && G > 0) {   // the step's scalars once per group (what cgl_d_step / cgl_mlp_backward do)
+    adam_scalars_kernel<<<(G + 127) / 128, 128, 0, (cudaStream_t)stream>>>(G, step, ids, lr, beta1, beta2, eps,
+                                                                          (AdamScalars*)adam_scratch);
+    CGL_CHECK_LAUNCH();
+    ad.scal = (const AdamScalars*)adam_scratch;
+  }
   CGL_CHECK_CUDA(run_linear_wgrad(G, rows, in, out, dy, dy_gstride, X, params, ld, ids, w_off, b_off, &ad,
                                   (cudaStream_t)stream));
   return CGL_OK;

@@ -125,6 +125,13 @@ static __global__ void adam_prepare_kernel(int G, int* step, const int* ids, flo
   step[row] = t;
   scal[g] = make_adam_scalars(t, lr, b1, b2, eps);
 }
+// the scalars alone, for a step counter that already includes the update (cgl_linear_wgrad_adam)
+static __global__ void adam_scalars_kernel(int G, const int* step, const int* ids, float lr, float b1, float b2,
+                                           float eps, AdamScalars* scal) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= G) return;
+  scal[g] = make_adam_scalars(step[ids ? ids[g] : g], lr, b1, b2, eps);
+}
 
 // dW[g][o][i] = sum_r dy[g][r][o] * x[g][r][i], db[g][o] = sum_r dy[g][r][o];
 // adam != NULL: applied in the epilogue as an Adam step on W / b (base = params);

@@ -28,6 +28,8 @@
 //   epilogue   : warps 0..7 wait done, tcgen05.ld 32x32b.x16 of every region, fused bias+activation /
 //                activation derivative / Adam, coalesced stores.
 #pragma once
+#include <stdlib.h>
+
 #include "gemm.cuh"
 
 namespace cgl {
@@ -39,6 +41,9 @@ constexpr int TC_LOADER_THREADS = 256;  // warps 0..7: operand staging, then the
 constexpr int TC_MMA_WARP = 8;          // warp 8: TMEM allocation and the single MMA-issuing thread
 constexpr int TC_THREADS = TC_LOADER_THREADS + 32;
 constexpr int TC_MAX_BN = 256;
+constexpr int TC_TUNE_DEFAULT = 1;
+constexpr int TC_PF_DIST = 256, TC_PF_CHUNK = 256;   // operand L2 prefetch: distance and chunk, in floats of K
+constexpr uint32_t TC_WAIT_HINT_NS = 20000u;
 
 // ---- PTX wrappers ----------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -55,11 +60,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   do {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
+        : "r"(bar), "r"(parity), "r"(TC_WAIT_HINT_NS)   // the thread may stay suspended this long: fewer polls,
+        : "memory");                                    // and the wake-up is still signalled by the barrier
     if (!ok && ++spins > (1ull << 26)) __trap();  // a lost arrival must fail loudly, not hang the GPU
   } while (!ok);
 }
@@ -109,6 +114,11 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// HBM -> L2 prefetch of `bytes` (multiple of 16, 16-byte aligned address): no registers, no completion to wait for
+__device__ __forceinline__ void l2_prefetch_bulk(const void* gptr, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
 }
 
 // hi = x rounded to tf32 (10 mantissa bits), round-half-up in magnitude: two integer instructions.
@@ -208,6 +218,7 @@ struct TcParams {
   const float* saved; long long saved_gstride;  // EPI_BWD_DATA: saved[g] + n*ldc + m
   float* adam_m; float* adam_v; const int* step; float lr, b1, b2, eps;  // EPI_ADAM
   const AdamScalars* scal;  // EPI_ADAM: [G] precomputed scalars of this step (NULL: derive from step)
+  int tune;  // bits (tc_tune()): 1 = L2 prefetch of the Adam tile under the main loop, 2 / 4 = L2 prefetch of the A / B operand
 };
 
 // TMEM plan (512 columns, 1 CTA per SM). The tensor core TRUNCATES when it adds into an fp32
@@ -374,6 +385,50 @@ __global__ void __launch_bounds__(TC_THREADS, OCC) tc_grouped_gemm_kernel(const 
     for (int d = 0; d < DEPTH; ++d)
       if (d < nkb) load_block(d, ra[d], rb[d]);
     if (warp == 0) TC_STAMP(2);
+    auto adam_tile_prefetch = [&]() {
+      if (!(EPI == EPI_ADAM && p.c_vec && (p.tune & 1))) return;
+      // the W / m / v tile this CTA streams in its epilogue (24 B per parameter, the HBM-bound part of a round)
+      // starts its way HBM -> L2 now, under the main loop: one row of the tile (<= 512 bytes) per request
+      const int n_valid = (p.N - n0 < bn) ? (p.N - n0) : bn;
+      const uint32_t m_bytes = (uint32_t)(((p.M - m0 < TC_BM) ? (p.M - m0) : TC_BM) * 4);
+      const long long tile0 = (long long)rowid * p.c_gstride + p.c_off + (long long)n0 * p.ldc + m0;
+      for (int n = tid; n < n_valid; n += TC_LOADER_THREADS) {
+        const long long off = tile0 + (long long)n * p.ldc;
+        l2_prefetch_bulk(p.cbase + off, m_bytes);
+        l2_prefetch_bulk(p.adam_m + off, m_bytes);
+        l2_prefetch_bulk(p.adam_v + off, m_bytes);
+      }
+    };
+    const int kb_prefetch = nkb > DEPTH ? nkb - DEPTH - 1 : 0;   // right after the last operand loads are issued
+
+    // Operand prefetch HBM -> L2, TC_PF_DIST..TC_PF_DIST+TC_PF_CHUNK floats of K ahead of the register loads: the
+    // weights are read exactly once, so every register load of W would otherwise pay the full HBM latency, and
+    // with 2-3 k-blocks in flight per thread (all the registers allow) the k-block time is latency / depth.
+    int pf_k = DEPTH * TC_BK;     // first k not yet requested by anyone
+    auto operand_prefetch = [&](int k_now) {
+      if (!(p.tune & 6) || pf_k >= p.K || k_now + TC_PF_DIST < pf_k) return;
+      const int k1 = (pf_k + TC_PF_CHUNK < p.K) ? pf_k + TC_PF_CHUNK : p.K;
+      if (p.tune & 2) {
+        if (A_KMAJOR) {   // 128 rows (m), each [pf_k, k1) contiguous
+          const int r = m0 + tid;
+          if (tid < TC_BM && r < p.M) l2_prefetch_bulk(row_ptr(RA, r) + pf_k, (uint32_t)(k1 - pf_k) * 4u);
+        } else {          // rows are k, each [m0, m0 + 128) contiguous
+          const uint32_t mb = (uint32_t)(((p.M - m0 < TC_BM) ? (p.M - m0) : TC_BM) * 4);
+          for (int k = pf_k + tid; k < k1; k += TC_LOADER_THREADS) l2_prefetch_bulk(row_ptr(RA, k) + m0, mb);
+        }
+      }
+      if (p.tune & 4) {
+        if (B_KMAJOR) {
+          const int r = n0 + tid;
+          if (tid < bn && r < p.N) l2_prefetch_bulk(row_ptr(RB, r) + pf_k, (uint32_t)(k1 - pf_k) * 4u);
+        } else {
+          const int nb4 = ((p.N - n0 < bn) ? (p.N - n0) : bn) * 4;
+          for (int k = pf_k + tid; k < k1; k += TC_LOADER_THREADS) l2_prefetch_bulk(row_ptr(RB, k) + n0, (uint32_t)nb4);
+        }
+      }
+      pf_k = k1;
+    };
+    operand_prefetch(0);
     for (int kb0 = 0; kb0 < nkb; kb0 += DEPTH) {
 #pragma unroll
       for (int d = 0; d < DEPTH; ++d) {
@@ -382,6 +437,8 @@ __global__ void __launch_bounds__(TC_THREADS, OCC) tc_grouped_gemm_kernel(const 
           store_block(ra[d], rb[d]);
           if (kb == 0 && warp == 0) TC_STAMP(3);
           if (kb + DEPTH < nkb) load_block(kb + DEPTH, ra[d], rb[d]);
+          if (kb == kb_prefetch) adam_tile_prefetch();
+          operand_prefetch((kb + 1) * TC_BK);
         }
       }
     }
@@ -641,9 +698,20 @@ static inline cudaError_t launch_tc_gemm_nb(const TcParams& p, int G, cudaStream
   return cudaGetLastError();
 }
 
+// CGL_TUNE=<bits> in the environment: experiment switches of the tcgen05 kernels (TcParams::tune)
+static inline int tc_tune() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CGL_TUNE");
+    v = e ? atoi(e) : TC_TUNE_DEFAULT;
+  }
+  return v;
+}
+
 template <bool A_KMAJOR, bool B_KMAJOR, int EPI>
 static inline cudaError_t launch_tc_gemm(TcParams p, int G, cudaStream_t stream) {
   if (G <= 0 || p.M <= 0 || p.N <= 0) return cudaSuccess;
+  p.tune = tc_tune();
   const int nks = (p.K + 7) / 8;
   if ((EPI == EPI_ADAM || EPI == EPI_STORE) && !A_KMAJOR && !B_KMAJOR && nks <= TC_MAX_ACCUM) {
     // short-K weight gradient: its epilogue (24 B per parameter for Adam) is the HBM-bound part of a round.

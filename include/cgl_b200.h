@@ -255,11 +255,13 @@ int cgl_linear_wgrad(int G, int rows, int in, int out, const float* dy, int64_t 
 
 /* Weight gradient with the Adam step fused into the epilogue (what cgl_d_step / cgl_mlp_backward run per layer):
  *   W[g] <- Adam(W[g], dy[g]^T x[g]),  b[g] <- Adam(b[g], colsum(dy[g]))   with torch.optim.Adam semantics (a7).
- * step[row(g)] must already hold the step count INCLUDING this update (the bias corrections use it).            */
+ * step[row(g)] must already hold the step count INCLUDING this update (the bias corrections use it).
+ * adam_scratch: NULL, or 32 * G bytes of device memory for the per-group scalars of the step (computed once per
+ * group by a small kernel instead of by every thread).                                                          */
 int cgl_linear_wgrad_adam(int G, int rows, int in, int out, const float* dy, int64_t dy_gstride, const float* x,
                           int64_t x_gstride, float* params, float* adam_m, float* adam_v, int64_t ld,
                           const int32_t* step, const int32_t* ids, int64_t w_off, int64_t b_off, float lr, float beta1,
-                          float beta2, float eps, cgl_stream_t stream);
+                          float beta2, float eps, void* adam_scratch, cgl_stream_t stream);
 
 #ifdef __cplusplus
 }

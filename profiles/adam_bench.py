@@ -24,12 +24,13 @@ x = torch.randn(G, rows, K, device="cuda")
 dy = torch.randn(G, rows, out, device="cuda") * 1e-3
 am, av = torch.zeros(G, ldp, device="cuda"), torch.zeros(G, ldp, device="cuda")
 step = torch.ones(G, dtype=torch.int32, device="cuda")
+scratch = torch.empty(G * 8, device="cuda")
 
 
 def run():
     abi.check(abi.lib.cgl_linear_wgrad_adam(G, rows, K, out, abi.ptr(dy), rows * out, abi.ptr(x), rows * K,
                                             abi.ptr(prm), abi.ptr(am), abi.ptr(av), ldp, abi.ptr(step), None, 0,
-                                            K * out, 2e-4, 0.5, 0.999, 1e-8, st()))
+                                            K * out, 2e-4, 0.5, 0.999, 1e-8, abi.ptr(scratch), st()))
 
 
 run()

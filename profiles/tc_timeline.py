@@ -25,6 +25,7 @@ dy = torch.randn(G, rows, out, device="cuda")
 grad = torch.zeros(G, ldp, device="cuda")
 am, av = torch.zeros(G, ldp, device="cuda"), torch.zeros(G, ldp, device="cuda")
 step = torch.ones(G, dtype=torch.int32, device="cuda")
+scratch = torch.empty(G * 8, device="cuda")
 
 
 def run():
@@ -37,7 +38,7 @@ def run():
     else:   # "adam": the fused weight-gradient + Adam epilogue
         abi.check(abi.lib.cgl_linear_wgrad_adam(G, rows, K, out, abi.ptr(dy), rows * out, abi.ptr(x), rows * K,
                                                 abi.ptr(prm), abi.ptr(am), abi.ptr(av), ldp, abi.ptr(step), None, 0,
-                                                K * out, 2e-4, 0.5, 0.999, 1e-8, st()))
+                                                K * out, 2e-4, 0.5, 0.999, 1e-8, abi.ptr(scratch), st()))
 
 
 run()
