@@ -4,7 +4,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libcgl_b200.so")
+# CGL_B200_LIB: another build of the same library (kernel variants compared under profiles/)
+LIB_PATH = os.environ.get("CGL_B200_LIB") or os.path.join(HERE, "lib", "libcgl_b200.so")
 
 MAX_LAYERS = 8
 ACT_NONE, ACT_LRELU, ACT_TANH, ACT_SIGMOID = 0, 1, 2, 3

@@ -8,7 +8,7 @@
 // can pin one for tests and profiling).
 #pragma once
 #include "builders.cuh"
-#include "tc_gemm.cuh"
+#include "tc_persist.cuh"
 
 namespace cgl {
 
@@ -74,6 +74,8 @@ static inline cudaError_t run_linear_fwd(int G, int rows, int in, int out, const
                (b_off < 0 || (aligned16(params) && ldp % 4 == 0 && b_off % 4 == 0))) ? 1 : 0;
     p.bias_base = (b_off >= 0) ? params : nullptr; p.bias_gstride = ldp; p.bias_idx = ids; p.bias_off = b_off;
     p.act = act; p.slope = slope;
+    cudaError_t pe = cudaSuccess;
+    if (launch_tc_persistent<true, true, EPI_FWD>(p, G, st, &pe)) return pe;
     return launch_tc_gemm<true, true, EPI_FWD>(p, G, st);
   }
   GemmParams p = fwd_params(rows, in, out, X, params, ldp, ids, w_off, b_off, act, slope, y, y_gstride);
@@ -100,7 +102,12 @@ static inline cudaError_t run_linear_bwd_data(int G, int rows, int in, int out, 
     p.c_vec = (aligned16(dx) && dx_gstride % 4 == 0 && in % 4 == 0 &&
                (!saved || (aligned16(saved) && saved_gstride % 4 == 0))) ? 1 : 0;
     p.saved = saved; p.saved_gstride = saved_gstride; p.act = act; p.slope = slope;
-    if (saved) return launch_tc_gemm<false, true, EPI_BWD_DATA>(p, G, st);
+    cudaError_t pe = cudaSuccess;
+    if (saved) {
+      if (launch_tc_persistent<false, true, EPI_BWD_DATA>(p, G, st, &pe)) return pe;
+      return launch_tc_gemm<false, true, EPI_BWD_DATA>(p, G, st);
+    }
+    if (launch_tc_persistent<false, true, EPI_STORE>(p, G, st, &pe)) return pe;
     return launch_tc_gemm<false, true, EPI_STORE>(p, G, st);
   }
   GemmParams p = bwd_data_params(rows, in, out, dy, dy_gstride, params, ldp, ids, w_off, saved, saved_gstride, act,

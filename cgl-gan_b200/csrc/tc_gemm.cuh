@@ -41,7 +41,7 @@ constexpr int TC_LOADER_THREADS = 256;  // warps 0..7: operand staging, then the
 constexpr int TC_MMA_WARP = 8;          // warp 8: TMEM allocation and the single MMA-issuing thread
 constexpr int TC_THREADS = TC_LOADER_THREADS + 32;
 constexpr int TC_MAX_BN = 256;
-constexpr int TC_TUNE_DEFAULT = 1;
+constexpr int TC_TUNE_DEFAULT = 1 | 8;
 constexpr int TC_PF_DIST = 256, TC_PF_CHUNK = 256;   // operand L2 prefetch: distance and chunk, in floats of K
 constexpr uint32_t TC_WAIT_HINT_NS = 20000u;
 
@@ -54,19 +54,39 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok = 0;
-  unsigned long long spins = 0;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity), "r"(TC_WAIT_HINT_NS)   // the thread may stay suspended this long: fewer polls,
-        : "memory");                                    // and the wake-up is still signalled by the barrier
-    if (!ok && ++spins > (1ull << 26)) __trap();  // a lost arrival must fail loudly, not hang the GPU
-  } while (!ok);
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(TC_WAIT_HINT_NS)   // the thread may stay suspended this long: fewer polls,
+      : "memory");                                    // and the wake-up is still signalled by the barrier
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  while (!mbar_try_wait(bar, parity)) {
+    unsigned long long t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (t1 - t0 > 2000000000ull) __trap();   // 2 s: a lost arrival must fail loudly, not hang the GPU
+  }
+}
+// a wait that lasts a whole main loop (the epilogue warps of the persistent kernel): back off between polls so the
+// waiting warp leaves the issue slots of its scheduler to the loaders
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(200);
+    unsigned long long t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (t1 - t0 > 2000000000ull) __trap();
+  }
 }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -218,7 +238,8 @@ struct TcParams {
   const float* saved; long long saved_gstride;  // EPI_BWD_DATA: saved[g] + n*ldc + m
   float* adam_m; float* adam_v; const int* step; float lr, b1, b2, eps;  // EPI_ADAM
   const AdamScalars* scal;  // EPI_ADAM: [G] precomputed scalars of this step (NULL: derive from step)
-  int tune;  // bits (tc_tune()): 1 = L2 prefetch of the Adam tile under the main loop, 2 / 4 = L2 prefetch of the A / B operand
+  int tune;  // bits (tc_tune()): 1 = L2 prefetch of the Adam tile under the main loop, 2 / 4 = L2 prefetch of the A / B
+             // operand, 8 / 16 = persistent kernel (tc_persist.cuh) for the data-gradient / forward product
 };
 
 // TMEM plan (512 columns, 1 CTA per SM). The tensor core TRUNCATES when it adds into an fp32
