@@ -82,6 +82,9 @@ lib.cgl_profile_summary.argtypes = [_i32, C.POINTER(C.c_double), C.POINTER(C.c_d
                                     C.POINTER(C.c_longlong)]
 lib.cgl_linear_wgrad_adam.argtypes = [_i32, _i32, _i32, _i32, _p, _i64, _p, _i64, _p, _p, _p, _i64, _p, _p, _i64, _i64,
                                       _f32, _f32, _f32, _f32, _p, _p]
+lib.cgl_gather_rows.argtypes = [_i64, _i32, _p, _i64, _p, _p, _p]
+lib.cgl_hist2d.argtypes = [_i64, _p, _i64, _p, _p]
+lib.cgl_kl_score_2d.argtypes = [_i64, _p, _i64, _p, _p, _p, _p]
 lib.cgl_set_gemm_mode.argtypes = [_i32]
 lib.cgl_debug_set_timeline.argtypes = [_p]
 lib.cgl_get_gemm_mode.restype = C.c_int
@@ -94,7 +97,8 @@ for _name in ("cgl_arch_describe", "cgl_mlp_layout_of", "cgl_d_step", "cgl_g_los
               "cgl_adam_rows", "cgl_mix_csr", "cgl_wsum", "cgl_bcast_mix", "cgl_comm_unique_id",
               "cgl_comm_init", "cgl_comm_destroy", "cgl_allreduce_sum", "cgl_mix_allreduce",
               "cgl_linear_fwd", "cgl_linear_bwd_data", "cgl_linear_wgrad", "cgl_set_gemm_mode", "cgl_mlp_forward", "cgl_mlp_backward", "cgl_profile_enable",
-              "cgl_profile_summary", "cgl_debug_set_timeline", "cgl_linear_wgrad_adam"):
+              "cgl_profile_summary", "cgl_debug_set_timeline", "cgl_linear_wgrad_adam", "cgl_gather_rows", "cgl_hist2d",
+              "cgl_kl_score_2d"):
     getattr(lib, _name).restype = C.c_int
 
 

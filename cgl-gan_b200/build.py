@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libcgl_b200.so")
-SOURCES = ["arch.cu", "dstep.cu", "gstep.cu", "mix.cu", "comm.cu"]
+SOURCES = ["arch.cu", "dstep.cu", "gstep.cu", "mix.cu", "comm.cu", "data.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared"]
 

@@ -1,0 +1,90 @@
+"""The data side path of a round, kept on the GPU.
+
+ResidentPartitions: the whole dataset lives in HBM once; every simulated client owns a list of row ids (its
+partition from partition.allocate_dataset). A round's real minibatches are produced exactly as the reference
+produces them -- `DataLoader(dataset, batch_size, shuffle=True)` per Worker, `next(self.data)`, a NEW DataLoader
+when the epoch is exhausted (CGLGAN/2DMG/main.py:299-301,350-355) -- except that the DataLoaders iterate over
+ROW IDS, not samples: same classes, same consumption of the torch global RNG, hence bit-identical batches, and
+only 8 bytes per sample travel host -> device; `cgl_gather_rows` assembles [C, B, d] on the GPU.
+shuffle=False gives the sequential full pass of FL-GAN (FLGAN/MNIST/flgan.py:250).
+
+kl_score_2d: plot_2d's KL score (CGLGAN/2DMG/main.py:68-94) on the GPU.
+"""
+import ctypes as C
+
+import torch
+from torch.utils.data import DataLoader
+
+from . import abi
+from .engine import _stream
+
+
+class ResidentPartitions:
+    def __init__(self, data, partitions, batch_size, device="cuda", shuffle=True):
+        """data: [n, ...] float tensor (moved to the device once); partitions: one sequence of row ids per client."""
+        abi.require_device()
+        self.device = torch.device(device)
+        self.n = data.shape[0]
+        self.data = data.reshape(self.n, -1).to(self.device, torch.float32).contiguous()
+        self.d = self.data.shape[1]
+        self.parts = [torch.as_tensor(p, dtype=torch.int64) for p in partitions]
+        self.C, self.B, self.shuffle = len(self.parts), int(batch_size), shuffle
+        # Worker.__init__: one DataLoader per client, created in client order (each iter() draws from the global RNG)
+        self.loaders = [DataLoader(dataset=p, batch_size=self.B, shuffle=shuffle) for p in self.parts]
+        self.iters = [iter(dl) for dl in self.loaders]
+        self._idx_host = torch.empty(self.C, self.B, dtype=torch.int64).pin_memory()
+        self._n_host = torch.empty(self.C, dtype=torch.int32).pin_memory()
+        self._idx_dev = torch.empty(self.C, self.B, dtype=torch.int64, device=self.device)
+        self._n_dev = torch.empty(self.C, dtype=torch.int32, device=self.device)
+
+    def next_indices(self):
+        """One `next(self.data)` per client, in client order (Worker.train, main.py:350-355). Returns the pinned
+        [C, B] row ids (-1 = padding of a short last batch) and the valid counts [C]."""
+        idx, n = self._idx_host, self._n_host
+        idx.fill_(-1)
+        for c in range(self.C):
+            try:
+                rows = next(self.iters[c])
+            except StopIteration:
+                self.loaders[c] = DataLoader(dataset=self.parts[c], batch_size=self.B, shuffle=self.shuffle)
+                self.iters[c] = iter(self.loaders[c])
+                rows = next(self.iters[c])
+            k = rows.numel()
+            idx[c, :k] = rows
+            n[c] = k
+        return idx, n
+
+    def next_batches(self, out=None):
+        """-> (real [C, B, d] on the device, n_real [C] int32 on the device) for MDStyleSim.round / FLStyleSim."""
+        idx, n = self.next_indices()
+        self._idx_dev.copy_(idx, non_blocking=True)
+        self._n_dev.copy_(n, non_blocking=True)
+        if out is None:
+            out = torch.empty(self.C, self.B, self.d, device=self.device)
+        abi.check(abi.lib.cgl_gather_rows(self.C * self.B, self.d, abi.ptr(self.data), self.n, abi.ptr(self._idx_dev),
+                                          abi.ptr(out), _stream()))
+        return out, self._n_dev
+
+    @property
+    def h2d_bytes_per_round(self):
+        return self.C * self.B * 8 + self.C * 4
+
+
+class KLScore2D:
+    """KL score of generated 2-D points against a fixed real sample (plot_2d, CGLGAN/2DMG/main.py:68-94)."""
+
+    def __init__(self, real_points, device="cuda"):
+        abi.require_device()
+        self.device = torch.device(device)
+        real = real_points.to(self.device, torch.float32).contiguous()
+        self.real_hist = torch.zeros(256, dtype=torch.int32, device=self.device)
+        self._scratch = torch.zeros(256, dtype=torch.int32, device=self.device)
+        self._out = torch.zeros(1, dtype=torch.float64, device=self.device)
+        abi.check(abi.lib.cgl_hist2d(real.shape[0], abi.ptr(real), real.shape[1], abi.ptr(self.real_hist), _stream()))
+
+    def __call__(self, points):
+        """points: [n, 2] device tensor -> 0-dim float64 device tensor."""
+        pts = points.to(self.device, torch.float32).contiguous()
+        abi.check(abi.lib.cgl_kl_score_2d(pts.shape[0], abi.ptr(pts), pts.shape[1], abi.ptr(self.real_hist),
+                                          abi.ptr(self._scratch), abi.ptr(self._out), _stream()))
+        return self._out[0].clone()

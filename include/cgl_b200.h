@@ -188,6 +188,20 @@ int cgl_wsum(int C, int64_t n, const float* w, const int32_t* rows, const float*
 int cgl_bcast_mix(int R, int64_t n, const int32_t* rows, float sigma, const float* g, float* dst,
                   int64_t ld_dst, cgl_stream_t stream);
 
+/* ---- data side path kept on the GPU ----------------------------------
+ * cgl_gather_rows: out[i,:] = data[idx[i],:] (idx[i] < 0: a row of zeros = the padding of a short last batch).
+ *   The dataset stays resident in HBM; the host reproduces DataLoader(shuffle=True)'s indices
+ *   (Worker.__init__ / Worker.train, CGLGAN/2DMG/main.py:299-301,350-355; the unshuffled full pass of
+ *   FLGAN/MNIST/flgan.py:250) and ships 8 bytes per sample instead of the sample.
+ * cgl_hist2d / cgl_kl_score_2d: plot_2d's quality score (CGLGAN/2DMG/main.py:68-94): np.histogram2d with
+ *   16 x 16 bins over [-1,1]^2 of n points (x at xy[i*stride], y at xy[i*stride+1]) and
+ *   scipy.stats.entropy(generated, real) over the bins the real set occupies (double, *out_kl on the device). */
+int cgl_gather_rows(int64_t n_out, int d, const float* data, int64_t n_rows, const int64_t* idx, float* out,
+                    cgl_stream_t stream);
+int cgl_hist2d(int64_t n, const float* xy, int64_t stride, uint32_t* hist256, cgl_stream_t stream);
+int cgl_kl_score_2d(int64_t n, const float* xy, int64_t stride, const uint32_t* real_hist256,
+                    uint32_t* scratch_hist256, double* out_kl, cgl_stream_t stream);
+
 /* ---- cross-GPU aggregation (the only collective on the path) --------------------------------
  * One process per GPU. rank 0 calls cgl_comm_unique_id, ships the 128 bytes to the other ranks
  * (torch.distributed broadcast), every rank calls cgl_comm_init. cgl_mix_allreduce computes the
