@@ -85,4 +85,4 @@ def test_cglgan_mnist_1024_clients_replication_and_oracle(lib, segema):
     again = after.clone()
     sim.cloud_aggregate()                       # all rows equal and the weights sum to 1: a fixed point
     torch.cuda.synchronize()
-    assert quantile_err(trunk.params.detach()[0], again[0], 1.0) < 1e-6
+    assert quantile_err(trunk.params.detach()[0], again[0], 1.0) < 256 * 2.0 ** -24
