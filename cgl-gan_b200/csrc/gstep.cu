@@ -76,6 +76,86 @@ __global__ void __launch_bounds__(128) bn_fwd_kernel(const BnFwdParams p) {
   }
 }
 
+// The same kernel with its 128-feature column block staged in shared memory first: every global load of the
+// block is in flight at once (16-byte cp.async, one 512-byte row segment per warp request) instead of three
+// dependent passes of 4-byte loads per thread; the arithmetic (and its order) is unchanged, so the results are
+// bit-identical. Needs rows * 512 bytes of shared memory and float4-addressable rows.
+__device__ __forceinline__ void bn_cp_async16(float* smem_dst, const float* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+               : "memory");
+}
+__device__ __forceinline__ void bn_cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+// tile[r][0..127] <- src[r * F + f0 .. f0 + 127] (zero beyond F), all 128 threads
+__device__ __forceinline__ void bn_stage_block(float* tile, const float* src, int rows, int F, int f0) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int f = f0 + lane * 4;
+  for (int r = warp; r < rows; r += 4) {
+    if (f < F) bn_cp_async16(tile + r * 128 + lane * 4, src + (long long)r * F + f);
+    else *reinterpret_cast<float4*>(tile + r * 128 + lane * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+__global__ void __launch_bounds__(128) bn_fwd_smem_kernel(const BnFwdParams p) {
+  extern __shared__ __align__(16) float bn_tile[];   // [rows][128]
+  const int g = blockIdx.y;
+  const int f0 = blockIdx.x * 128;
+  const int t = threadIdx.x;
+  const int f = f0 + t;
+  const int n = p.rows;
+  bn_stage_block(bn_tile, p.u + (long long)g * p.u_gstride, n, p.F, f0);
+  bn_cp_async_wait_all();
+  __syncthreads();
+  if (f >= p.F) return;
+  const int rowid = p.ids ? p.ids[g] : g;
+  const float* u = bn_tile + t;                      // this thread's column, stride 128
+  float* h = p.h + (long long)g * p.h_gstride + f;
+  const float gamma = __ldg(p.params + (long long)rowid * p.ldp + p.gamma_off + f);
+  const float beta = __ldg(p.params + (long long)rowid * p.ldp + p.beta_off + f);
+  float mean, var;
+  if (p.train) {
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int r = 0;
+    for (; r + 3 < n; r += 4) {
+      s0 += u[r * 128]; s1 += u[(r + 1) * 128];
+      s2 += u[(r + 2) * 128]; s3 += u[(r + 3) * 128];
+    }
+    for (; r < n; ++r) s0 += u[r * 128];
+    mean = ((s0 + s1) + (s2 + s3)) / (float)n;
+    s0 = s1 = s2 = s3 = 0.f;
+    r = 0;
+    for (; r + 3 < n; r += 4) {
+      float d0 = u[r * 128] - mean, d1 = u[(r + 1) * 128] - mean;
+      float d2 = u[(r + 2) * 128] - mean, d3 = u[(r + 3) * 128] - mean;
+      s0 = fmaf(d0, d0, s0); s1 = fmaf(d1, d1, s1); s2 = fmaf(d2, d2, s2); s3 = fmaf(d3, d3, s3);
+    }
+    for (; r < n; ++r) { float d0 = u[r * 128] - mean; s0 = fmaf(d0, d0, s0); }
+    const float ss = (s0 + s1) + (s2 + s3);
+    var = ss / (float)n;
+    if (p.stats) {
+      float* rm = p.stats + (long long)rowid * p.ld_stats + p.mean_off + f;
+      float* rv = p.stats + (long long)rowid * p.ld_stats + p.var_off + f;
+      const float unbiased = n > 1 ? ss / (float)(n - 1) : var;
+      *rm = (1.f - p.momentum) * *rm + p.momentum * mean;
+      *rv = (1.f - p.momentum) * *rv + p.momentum * unbiased;
+    }
+  } else {
+    mean = p.stats[(long long)rowid * p.ld_stats + p.mean_off + f];
+    var = p.stats[(long long)rowid * p.ld_stats + p.var_off + f];
+  }
+  const float invstd = 1.f / sqrtf(var + p.eps);
+  if (p.save_mean) {
+    p.save_mean[(long long)g * p.F + f] = mean;
+    p.save_invstd[(long long)g * p.F + f] = invstd;
+  }
+  const float a = invstd * gamma;
+  for (int r = 0; r < n; ++r) {
+    const float y = (u[r * 128] - mean) * a + beta;
+    h[(long long)r * p.F] = act_fwd(y, p.act, p.slope);
+  }
+}
+
 // Backward of the same: dz is the gradient wrt the BatchNorm OUTPUT (activation derivative already
 // applied); overwritten in place with the gradient wrt the BatchNorm input u. gamma / beta take
 // their Adam step here (torch.optim.Adam on bn.weight / bn.bias).
@@ -137,6 +217,69 @@ __global__ void __launch_bounds__(128) bn_bwd_kernel(const BnBwdParams p) {
     adam_update(w, mm, vv, dbeta, s);
     p.params[bo] = w; p.adam_m[bo] = mm; p.adam_v[bo] = vv;
   }
+}
+
+// bn_bwd_kernel with dz and u staged in shared memory (see bn_fwd_smem_kernel): 2 * rows * 512 bytes, same arithmetic.
+__global__ void __launch_bounds__(128) bn_bwd_smem_kernel(const BnBwdParams p) {
+  extern __shared__ __align__(16) float bn_tile[];   // dz [rows][128] | u [rows][128]
+  const int g = blockIdx.y;
+  const int f0 = blockIdx.x * 128;
+  const int t = threadIdx.x;
+  const int f = f0 + t;
+  const int n = p.rows;
+  float* tz = bn_tile;
+  float* tu = bn_tile + n * 128;
+  bn_stage_block(tz, p.dz + (long long)g * p.dz_gstride, n, p.F, f0);
+  bn_stage_block(tu, p.u + (long long)g * p.u_gstride, n, p.F, f0);
+  bn_cp_async_wait_all();
+  __syncthreads();
+  if (f >= p.F) return;
+  const int rowid = p.ids ? p.ids[g] : g;
+  float* dzg = p.dz + (long long)g * p.dz_gstride + f;
+  const float* dz = tz + t;
+  const float* u = tu + t;
+  const float mean = p.save_mean[(long long)g * p.F + f];
+  const float invstd = p.save_invstd[(long long)g * p.F + f];
+  float sb0 = 0.f, sb1 = 0.f, sg0 = 0.f, sg1 = 0.f;
+  int r = 0;
+  for (; r + 1 < n; r += 2) {
+    const float d0 = dz[r * 128], d1 = dz[(r + 1) * 128];
+    sb0 += d0; sb1 += d1;
+    sg0 = fmaf(d0, u[r * 128] - mean, sg0);
+    sg1 = fmaf(d1, u[(r + 1) * 128] - mean, sg1);
+  }
+  for (; r < n; ++r) {
+    const float d0 = dz[r * 128];
+    sb0 += d0;
+    sg0 = fmaf(d0, u[r * 128] - mean, sg0);
+  }
+  const float dbeta = sb0 + sb1;
+  const float dotp = sg0 + sg1;
+  const float dgamma = dotp * invstd;
+  const long long go = (long long)rowid * p.ldp + p.gamma_off + f;
+  const long long bo = (long long)rowid * p.ldp + p.beta_off + f;
+  const float gamma = p.params[go];
+  const float k = dotp * invstd * invstd / (float)n;
+  const float mb = dbeta / (float)n;
+  const float a = invstd * gamma;
+  for (r = 0; r < n; ++r) dzg[(long long)r * p.F] = (dz[r * 128] - mb - (u[r * 128] - mean) * k) * a;
+  const AdamScalars s = p.scal ? p.scal[g] : make_adam_scalars(p.step[rowid], p.lr, p.b1, p.b2, p.eps);
+  {
+    float w = gamma, mm = p.adam_m[go], vv = p.adam_v[go];
+    adam_update(w, mm, vv, dgamma, s);
+    p.params[go] = w; p.adam_m[go] = mm; p.adam_v[go] = vv;
+  }
+  {
+    float w = p.params[bo], mm = p.adam_m[bo], vv = p.adam_v[bo];
+    adam_update(w, mm, vv, dbeta, s);
+    p.params[bo] = w; p.adam_m[bo] = mm; p.adam_v[bo] = vv;
+  }
+}
+
+// shared-memory variants apply when the block fits and the rows are float4-addressable
+static inline bool bn_smem_ok(int rows, int F, const void* a, long long a_gs, const void* b, long long b_gs, int arrays) {
+  return (size_t)arrays * rows * 512 <= 200 * 1024 && F % 4 == 0 && aligned16(a) && a_gs % 4 == 0 &&
+         (!b || (aligned16(b) && b_gs % 4 == 0));
 }
 
 // dz = dy * act'(y), y the saved activation output (the Tanh of the generator's last layer)
@@ -250,7 +393,16 @@ extern "C" int cgl_mlp_forward(const cgl_mlp_desc* arch, int G, const float* par
       b.act = arch->act[l]; b.slope = arch->lrelu_slope;
       dim3 grid((out + 127) / 128, G);
       ProfScope prof(CGL_PROF_BN_FWD, 8.0 * G * rows * (double)out, 0.0, st);   // u read, h written
-      bn_fwd_kernel<<<grid, 128, 0, st>>>(b);
+      if (bn_smem_ok(rows, out, b.u, b.u_gstride, nullptr, 0, 1)) {
+        static bool attr = false;
+        if (!attr) {
+          CGL_CHECK_CUDA(cudaFuncSetAttribute(bn_fwd_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+          attr = true;
+        }
+        bn_fwd_smem_kernel<<<grid, 128, (size_t)rows * 512, st>>>(b);
+      } else {
+        bn_fwd_kernel<<<grid, 128, 0, st>>>(b);
+      }
       CGL_CHECK_LAUNCH();
     }
   }
@@ -308,7 +460,16 @@ extern "C" int cgl_mlp_backward(const cgl_mlp_desc* arch, int G, float* params, 
       b.step = step; b.lr = cfg->lr; b.b1 = cfg->beta1; b.b2 = cfg->beta2; b.eps = cfg->eps; b.scal = w.scal;
       dim3 grid((out + 127) / 128, G);
       ProfScope prof(CGL_PROF_BN_BWD, 12.0 * G * rows * (double)out, 0.0, st);  // dz, u read, du written
-      bn_bwd_kernel<<<grid, 128, 0, st>>>(b);
+      if (bn_smem_ok(rows, out, b.dz, b.dz_gstride, b.u, b.u_gstride, 2)) {
+        static bool attr = false;
+        if (!attr) {
+          CGL_CHECK_CUDA(cudaFuncSetAttribute(bn_bwd_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+          attr = true;
+        }
+        bn_bwd_smem_kernel<<<grid, 128, (size_t)rows * 1024, st>>>(b);
+      } else {
+        bn_bwd_kernel<<<grid, 128, 0, st>>>(b);
+      }
       CGL_CHECK_LAUNCH();
     }
     // data gradient first: it reads W_l, which the weight-gradient kernel below overwrites (fused Adam)

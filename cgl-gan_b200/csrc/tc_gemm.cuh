@@ -41,7 +41,7 @@ constexpr int TC_LOADER_THREADS = 256;  // warps 0..7: operand staging, then the
 constexpr int TC_MMA_WARP = 8;          // warp 8: TMEM allocation and the single MMA-issuing thread
 constexpr int TC_THREADS = TC_LOADER_THREADS + 32;
 constexpr int TC_MAX_BN = 256;
-constexpr int TC_TUNE_DEFAULT = 1 | 8;
+constexpr int TC_TUNE_DEFAULT = 1 | 8 | 32;
 constexpr int TC_PF_DIST = 256, TC_PF_CHUNK = 256;   // operand L2 prefetch: distance and chunk, in floats of K
 constexpr uint32_t TC_WAIT_HINT_NS = 20000u;
 
@@ -239,7 +239,8 @@ struct TcParams {
   float* adam_m; float* adam_v; const int* step; float lr, b1, b2, eps;  // EPI_ADAM
   const AdamScalars* scal;  // EPI_ADAM: [G] precomputed scalars of this step (NULL: derive from step)
   int tune;  // bits (tc_tune()): 1 = L2 prefetch of the Adam tile under the main loop, 2 / 4 = L2 prefetch of the A / B
-             // operand, 8 / 16 = persistent kernel (tc_persist.cuh) for the data-gradient / forward product
+             // operand, 8 / 16 = persistent kernel (tc_persist.cuh) for the data-gradient / forward product,
+             // 32 / 64 = 16 loader warps in the one-tile forward / data-gradient kernel
 };
 
 // TMEM plan (512 columns, 1 CTA per SM). The tensor core TRUNCATES when it adds into an fp32
@@ -262,8 +263,14 @@ __host__ __device__ inline int tc_n_main(int bn) {
 // NB = B patches per loader warp (4: bn <= 128, 8: bn <= 256); 8 loader warps + 1 MMA warp.
 // OCC = CTAs per SM the variant is built for. OCC 2 (short-K weight gradients: one stage, half of TMEM, fewer
 // registers) lets one CTA's HBM-bound Adam epilogue run under another CTA's main loop.
-template <bool A_KMAJOR, bool B_KMAJOR, int EPI, int NB, int OCC>
-__global__ void __launch_bounds__(TC_THREADS, OCC) tc_grouped_gemm_kernel(const TcParams p) {
+// LW = loader warps (8, or 16 for the long-K one-CTA-per-SM variants: the loader loop is ~330 instructions per
+// k-block at ~0.35 IPC per scheduler with two warps each, so four warps per scheduler hide more of its latency)
+template <bool A_KMAJOR, bool B_KMAJOR, int EPI, int NB, int OCC, int LW>
+__global__ void __launch_bounds__(LW * 32 + 32, OCC) tc_grouped_gemm_kernel(const TcParams p) {
+  constexpr int LT = LW * 32;          // loader (= epilogue) threads
+  constexpr int MMAW = LW;             // the warp after them allocates TMEM and issues the MMAs
+  constexpr int NA = 32 / LW;          // A patches per loader warp (a 128-line tile has 32)
+  constexpr int NBW = NB * 8 / LW;     // B patches per loader warp
   extern __shared__ __align__(1024) char tc_smem[];
   __shared__ __align__(8) unsigned long long bar_full[TC_MAX_STAGES];
   __shared__ __align__(8) unsigned long long bar_empty[TC_MAX_STAGES];
@@ -294,20 +301,20 @@ __global__ void __launch_bounds__(TC_THREADS, OCC) tc_grouped_gemm_kernel(const 
 
   if (tid == 0) {
     for (int i = 0; i < nst; ++i) {
-      mbar_init(smem_u32(&bar_full[i]), TC_LOADER_THREADS);
+      mbar_init(smem_u32(&bar_full[i]), LT);
       mbar_init(smem_u32(&bar_empty[i]), 1);
     }
     mbar_init(smem_u32(&bar_done), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == TC_MMA_WARP) tmem_alloc(smem_u32(&tmem_slot), tmem_cols);
+  if (warp == MMAW) tmem_alloc(smem_u32(&tmem_slot), tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = tmem_slot;
   if (warp == 0) TC_STAMP(1);
 
-  if (warp == TC_MMA_WARP) {
+  if (warp == MMAW) {
     // ===== MMA issuer: one thread =====
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_tf32(!A_KMAJOR, !B_KMAJOR, bn);
@@ -351,7 +358,7 @@ __global__ void __launch_bounds__(TC_THREADS, OCC) tc_grouped_gemm_kernel(const 
   } else {
     // epilogue operands that do not depend on the accumulator are requested now, under the main loop
     const int q = warp & 3;        // TMEM lane quarter this warp may read
-    const int half = warp >> 2;    // warps w and w+4 share a quarter and alternate 16-column chunks
+    const int half = warp >> 2;    // the LW/4 warps of a quarter take the 16-column chunks in turn
     const int m = m0 + q * 32 + lane;
     const bool m_ok = m < p.M;
     const int rowid = p.cidx ? p.cidx[g] : g;
@@ -367,32 +374,32 @@ __global__ void __launch_bounds__(TC_THREADS, OCC) tc_grouped_gemm_kernel(const 
     const Rows RA = resolve(p.A, g);
     const Rows RB = resolve(p.B, g);
     const int npb = bn_pad >> 2;  // patches of the B tile (K-major tiles beyond bn are zero-filled)
-    constexpr int DEPTH = (NB == 4 && OCC == 1) ? 3 : 2;  // k-blocks of global loads in flight per thread
-    float4 ra[DEPTH][4], rb[DEPTH][NB];
-    auto load_block = [&](int kb, float4 (&qa)[4], float4 (&qb)[NB]) {
+    constexpr int DEPTH = (LW == 16) ? 4 : ((NB == 4 && OCC == 1) ? 3 : 2);  // k-blocks of global loads in flight per thread
+    float4 ra[DEPTH][NA], rb[DEPTH][NBW];
+    auto load_block = [&](int kb, float4 (&qa)[NA], float4 (&qb)[NBW]) {
       const int k0 = kb * TC_BK;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) qa[i] = tc_patch_load<A_KMAJOR>(RA, warp + 8 * i, lane, m0, p.M, k0, p.K);
+      for (int i = 0; i < NA; ++i) qa[i] = tc_patch_load<A_KMAJOR>(RA, warp + LW * i, lane, m0, p.M, k0, p.K);
 #pragma unroll
-      for (int i = 0; i < NB; ++i) {
-        const int pp = warp + 8 * i;
+      for (int i = 0; i < NBW; ++i) {
+        const int pp = warp + LW * i;
         qb[i] = (pp < npb) ? tc_patch_load<B_KMAJOR>(RB, pp, lane, n0, p.N, k0, p.K) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
     int st_s = 0;            // stage of the next store
     uint32_t st_par = 1;     // parity to wait for on empty[st_s]; nothing to wait for during the first pass
     bool st_first = true;
-    auto store_block = [&](const float4 (&qa)[4], const float4 (&qb)[NB]) {
+    auto store_block = [&](const float4 (&qa)[NA], const float4 (&qb)[NBW]) {
       if (!st_first) mbar_wait(smem_u32(&bar_empty[st_s]), st_par);  // MMAs that read this stage are done
       char* a_hi = smem + (size_t)st_s * stage_bytes;
       char* a_lo = a_hi + a_bytes;
       char* b_hi = a_hi + 2 * a_bytes;
       char* b_lo = b_hi + b_bytes;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) tc_split_store(a_hi, a_lo, tc_patch_offset<A_KMAJOR>(warp + 8 * i, lane), qa[i]);
+      for (int i = 0; i < NA; ++i) tc_split_store(a_hi, a_lo, tc_patch_offset<A_KMAJOR>(warp + LW * i, lane), qa[i]);
 #pragma unroll
-      for (int i = 0; i < NB; ++i) {
-        const int pp = warp + 8 * i;
+      for (int i = 0; i < NBW; ++i) {
+        const int pp = warp + LW * i;
         if (pp < npb) tc_split_store(b_hi, b_lo, tc_patch_offset<B_KMAJOR>(pp, lane), qb[i]);
       }
       fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core (async proxy)
@@ -413,7 +420,7 @@ __global__ void __launch_bounds__(TC_THREADS, OCC) tc_grouped_gemm_kernel(const 
       const int n_valid = (p.N - n0 < bn) ? (p.N - n0) : bn;
       const uint32_t m_bytes = (uint32_t)(((p.M - m0 < TC_BM) ? (p.M - m0) : TC_BM) * 4);
       const long long tile0 = (long long)rowid * p.c_gstride + p.c_off + (long long)n0 * p.ldc + m0;
-      for (int n = tid; n < n_valid; n += TC_LOADER_THREADS) {
+      for (int n = tid; n < n_valid; n += LT) {
         const long long off = tile0 + (long long)n * p.ldc;
         l2_prefetch_bulk(p.cbase + off, m_bytes);
         l2_prefetch_bulk(p.adam_m + off, m_bytes);
@@ -435,7 +442,7 @@ __global__ void __launch_bounds__(TC_THREADS, OCC) tc_grouped_gemm_kernel(const 
           if (tid < TC_BM && r < p.M) l2_prefetch_bulk(row_ptr(RA, r) + pf_k, (uint32_t)(k1 - pf_k) * 4u);
         } else {          // rows are k, each [m0, m0 + 128) contiguous
           const uint32_t mb = (uint32_t)(((p.M - m0 < TC_BM) ? (p.M - m0) : TC_BM) * 4);
-          for (int k = pf_k + tid; k < k1; k += TC_LOADER_THREADS) l2_prefetch_bulk(row_ptr(RA, k) + m0, mb);
+          for (int k = pf_k + tid; k < k1; k += LT) l2_prefetch_bulk(row_ptr(RA, k) + m0, mb);
         }
       }
       if (p.tune & 4) {
@@ -444,7 +451,7 @@ __global__ void __launch_bounds__(TC_THREADS, OCC) tc_grouped_gemm_kernel(const 
           if (tid < bn && r < p.N) l2_prefetch_bulk(row_ptr(RB, r) + pf_k, (uint32_t)(k1 - pf_k) * 4u);
         } else {
           const int nb4 = ((p.N - n0 < bn) ? (p.N - n0) : bn) * 4;
-          for (int k = pf_k + tid; k < k1; k += TC_LOADER_THREADS) l2_prefetch_bulk(row_ptr(RB, k) + n0, (uint32_t)nb4);
+          for (int k = pf_k + tid; k < k1; k += LT) l2_prefetch_bulk(row_ptr(RB, k) + n0, (uint32_t)nb4);
         }
       }
       pf_k = k1;
@@ -524,24 +531,24 @@ __global__ void __launch_bounds__(TC_THREADS, OCC) tc_grouped_gemm_kernel(const 
       // stream W / m / v as float4 along m: 512 contiguous bytes per warp request and UNR*3 independent 16-byte
       // loads in flight per thread, instead of 4-byte accesses that leave the memory pipeline mostly empty.
       float* T = reinterpret_cast<float*>(smem);
-      for (int c = half; chunk_ok(c); c += 2) {
+      for (int c = half; chunk_ok(c); c += LW / 4) {
         float gv[16];
         tmem_chunk(c, gv);
 #pragma unroll
         for (int j = 0; j < 16; ++j) T[(c * 16 + j) * TC_BM + q * 32 + lane] = gv[j];
       }
-      asm volatile("bar.sync 1, %0;" ::"n"(TC_LOADER_THREADS) : "memory");  // the 8 loader / epilogue warps only
+      asm volatile("bar.sync 1, %0;" ::"n"(LT) : "memory");  // the 8 loader / epilogue warps only
       const int n_valid = (p.N - n0 < bn) ? (p.N - n0) : bn;
       const int m4_valid = ((p.M - m0 < TC_BM) ? (p.M - m0) : TC_BM) >> 2;   // M % 4 == 0 (MN-major A operand)
       const int items = n_valid * (TC_BM / 4);
       constexpr int UNR = (OCC == 2) ? 3 : 4;
-      for (int i0 = tid; i0 < items; i0 += TC_LOADER_THREADS * UNR) {
+      for (int i0 = tid; i0 < items; i0 += LT * UNR) {
         float4 w4[UNR], a4[UNR], v4[UNR];
         long long off[UNR];
         bool ok[UNR];
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
-          const int i = i0 + u * TC_LOADER_THREADS;
+          const int i = i0 + u * LT;
           const int n = i >> 5, mq = i & 31;
           ok[u] = i < items && mq < m4_valid;
           off[u] = (long long)(n0 + n) * p.ldc + m0 + mq * 4;
@@ -554,7 +561,7 @@ __global__ void __launch_bounds__(TC_THREADS, OCC) tc_grouped_gemm_kernel(const 
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
           if (ok[u]) {
-            const int i = i0 + u * TC_LOADER_THREADS;
+            const int i = i0 + u * LT;
             const float4 g4 = *reinterpret_cast<const float4*>(T + (i >> 5) * TC_BM + (i & 31) * 4);
             adam_update_fast(w4[u].x, a4[u].x, v4[u].x, g4.x, as);
             adam_update_fast(w4[u].y, a4[u].y, v4[u].y, g4.y, as);
@@ -568,7 +575,7 @@ __global__ void __launch_bounds__(TC_THREADS, OCC) tc_grouped_gemm_kernel(const 
       }
     } else if (EPI == EPI_ADAM) {
       // unaligned packed rows: scalar accesses, one TMEM chunk at a time
-      for (int c = half; chunk_ok(c); c += 2) {
+      for (int c = half; chunk_ok(c); c += LW / 4) {
         const int nb = n0 + c * 16;
         float g[16];
         tmem_chunk(c, g);
@@ -595,13 +602,13 @@ __global__ void __launch_bounds__(TC_THREADS, OCC) tc_grouped_gemm_kernel(const 
       // same route for the other epilogues: accumulators to shared ([n][m]), then float4 rows of the output
       // (512 contiguous bytes per warp store; bias / saved activations as float4 too)
       float* T = reinterpret_cast<float*>(smem);
-      for (int c = half; chunk_ok(c); c += 2) {
+      for (int c = half; chunk_ok(c); c += LW / 4) {
         float gv[16];
         tmem_chunk(c, gv);
 #pragma unroll
         for (int j = 0; j < 16; ++j) T[(c * 16 + j) * TC_BM + q * 32 + lane] = gv[j];
       }
-      asm volatile("bar.sync 1, %0;" ::"n"(TC_LOADER_THREADS) : "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(LT) : "memory");
       const int n_valid = (p.N - n0 < bn) ? (p.N - n0) : bn;
       const int m4_valid = ((p.M - m0 < TC_BM) ? (p.M - m0) : TC_BM) >> 2;   // M % 4 == 0 with c_vec
       const int items = n_valid * (TC_BM / 4);
@@ -612,19 +619,19 @@ __global__ void __launch_bounds__(TC_THREADS, OCC) tc_grouped_gemm_kernel(const 
         b4 = __ldg(reinterpret_cast<const float4*>(p.bias_base + (long long)brow * p.bias_gstride + p.bias_off + m0 + mq * 4));
       }
       constexpr int UNR = 4;
-      for (int i0 = tid; i0 < items; i0 += TC_LOADER_THREADS * UNR) {
+      for (int i0 = tid; i0 < items; i0 += LT * UNR) {
         float4 s4[UNR];
         if (EPI == EPI_BWD_DATA && S) {
 #pragma unroll
           for (int u = 0; u < UNR; ++u) {
-            const int i = i0 + u * TC_LOADER_THREADS;
+            const int i = i0 + u * LT;
             if (i < items && mq < m4_valid)
               s4[u] = __ldg(reinterpret_cast<const float4*>(S + (long long)(n0 + (i >> 5)) * p.ldc + m0 + mq * 4));
           }
         }
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
-          const int i = i0 + u * TC_LOADER_THREADS;
+          const int i = i0 + u * LT;
           if (i < items && mq < m4_valid) {
             float4 o = *reinterpret_cast<const float4*>(T + (i >> 5) * TC_BM + mq * 4);
             if (EPI == EPI_FWD) {
@@ -640,7 +647,7 @@ __global__ void __launch_bounds__(TC_THREADS, OCC) tc_grouped_gemm_kernel(const 
         }
       }
     } else {
-      for (int c = half; chunk_ok(c); c += 2) {
+      for (int c = half; chunk_ok(c); c += LW / 4) {
         const int nb = n0 + c * 16;
         float v[16];
         tmem_chunk(c, v);
@@ -671,7 +678,7 @@ __global__ void __launch_bounds__(TC_THREADS, OCC) tc_grouped_gemm_kernel(const 
   if (warp == 0) TC_STAMP(6);
   tc_fence_before();
   __syncthreads();
-  if (warp == TC_MMA_WARP) tmem_dealloc(tmem_d, tmem_cols);
+  if (warp == MMAW) tmem_dealloc(tmem_d, tmem_cols);
   if (warp == 0) TC_STAMP(7);
 }
 
@@ -703,18 +710,18 @@ static inline int tc_pow2_cols(int cols) {
   return c;
 }
 
-template <bool A_KMAJOR, bool B_KMAJOR, int EPI, int NB, int OCC>
+template <bool A_KMAJOR, bool B_KMAJOR, int EPI, int NB, int OCC, int LW = 8>
 static inline cudaError_t launch_tc_gemm_nb(const TcParams& p, int G, cudaStream_t stream) {
   static bool attr_set = false;  // per template instantiation
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tc_grouped_gemm_kernel<A_KMAJOR, B_KMAJOR, EPI, NB, OCC>,
+    cudaError_t e = cudaFuncSetAttribute(tc_grouped_gemm_kernel<A_KMAJOR, B_KMAJOR, EPI, NB, OCC, LW>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BUDGET);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
   const size_t smem = (size_t)p.n_stages * tc_stage_bytes(p.bn) + 1024;
   dim3 grid((p.N + p.bn - 1) / p.bn, (p.M + TC_BM - 1) / TC_BM, G);
-  tc_grouped_gemm_kernel<A_KMAJOR, B_KMAJOR, EPI, NB, OCC><<<grid, TC_THREADS, smem, stream>>>(p);
+  tc_grouped_gemm_kernel<A_KMAJOR, B_KMAJOR, EPI, NB, OCC, LW><<<grid, LW * 32 + 32, smem, stream>>>(p);
   count_launch();
   return cudaGetLastError();
 }
@@ -748,6 +755,8 @@ static inline cudaError_t launch_tc_gemm(TcParams p, int G, cudaStream_t stream)
   p.n_stages = tc_pick_stages(p.bn);
   p.n_main = tc_n_main(p.bn);
   p.tmem_cols = TC_TMEM_COLS;
+  if (p.bn <= 128 && EPI == EPI_FWD && (p.tune & 32)) return launch_tc_gemm_nb<A_KMAJOR, B_KMAJOR, EPI_FWD, 4, 1, 16>(p, G, stream);
+  if (p.bn <= 128 && !A_KMAJOR && B_KMAJOR && (p.tune & 64)) return launch_tc_gemm_nb<A_KMAJOR, B_KMAJOR, EPI, 4, 1, 16>(p, G, stream);
   if (p.bn <= 128) return launch_tc_gemm_nb<A_KMAJOR, B_KMAJOR, EPI, 4, 1>(p, G, stream);
   return launch_tc_gemm_nb<A_KMAJOR, B_KMAJOR, EPI, 8, 1>(p, G, stream);
 }
