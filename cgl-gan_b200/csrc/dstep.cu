@@ -181,6 +181,193 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(const HeadParams p) 
   }
 }
 
+// The same head as ONE pass over the last hidden layer: the activations travel global -> shared in chunks of
+// HEAD_CH rows (16-byte cp.async, double-buffered: the next chunk is in flight while this one is consumed), and the
+// three consumers of a row -- its logits, dZ of the hidden layer, and the last layer's weight gradient -- read it
+// from there. head_kernel reads the 200 x 256 block three times with dependent 4-byte loads (1.4 TB/s); the
+// arithmetic and its order are unchanged (rows ascending, the same warp reduction), so the results are bit-identical.
+// Needs H % 4 == 0, H <= 1024 (weight-gradient accumulators stay in registers) and float4-addressable rows.
+constexpr int HEAD_CH = 50;
+constexpr int HEAD_MAXJ = 4;   // H / HEAD_THREADS
+
+__global__ void __launch_bounds__(HEAD_THREADS) head_stream_kernel(const HeadParams p) {
+  extern __shared__ __align__(16) float smem[];
+  const int H = p.H, nout = p.nout;
+  float* tile0 = smem;                       // [HEAD_CH][H]
+  float* tile1 = tile0 + HEAD_CH * H;        // [HEAD_CH][H]
+  float* sW = tile1 + HEAD_CH * H;           // [nout][H]
+  float* sdz = sW + nout * H;                // [rows][nout]
+  float* sloss = sdz + p.rows * nout;        // [rows]
+  float* sb = sloss + p.rows;                // [nout]
+
+  const int g = blockIdx.x;
+  const int rowid = p.ids ? p.ids[g] : g;
+  float* W = p.params + (long long)rowid * p.ldp + p.w_off;
+  float* Bv = p.params + (long long)rowid * p.ldp + p.b_off;
+  const float* hin = p.hin + (long long)g * p.hin_gstride;
+  float* dz = p.dz + (long long)g * p.dz_gstride;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nwarp = HEAD_THREADS / 32;
+  const int nchunks = (p.rows + HEAD_CH - 1) / HEAD_CH;
+
+  auto issue_chunk = [&](int c) {
+    float* T = (c & 1) ? tile1 : tile0;
+    const int r0 = c * HEAD_CH;
+    const int nr = min(HEAD_CH, p.rows - r0);
+    const float* src = hin + (long long)r0 * H;
+    for (int i = tid; i < nr * (H >> 2); i += HEAD_THREADS)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(T + 4 * i)),
+                   "l"(src + 4 * i) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  issue_chunk(0);
+  for (int i = tid; i < nout * H; i += HEAD_THREADS) sW[i] = W[i];
+  if (tid < nout) sb[tid] = Bv[tid];
+
+  const int nv0 = p.n_valid0 ? min(p.n_valid0[g], p.rows0) : p.rows0;
+  const int n1 = p.rows - p.rows0;
+  float g0[HEAD_MAXJ], g1[HEAD_MAXJ];
+#pragma unroll
+  for (int j = 0; j < HEAD_MAXJ; ++j) { g0[j] = 0.f; g1[j] = 0.f; }
+
+  for (int c = 0; c < nchunks; ++c) {
+    if (c + 1 < nchunks) {
+      issue_chunk(c + 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();                         // chunk c (and, the first time, sW / sb) visible to every thread
+    const float* T = (c & 1) ? tile1 : tile0;
+    const int r0 = c * HEAD_CH;
+    const int nr = min(HEAD_CH, p.rows - r0);
+
+    // ---- logits, loss terms, d loss / d logits of the chunk's rows ----
+    for (int r = r0 + warp; r < r0 + nr; r += nwarp) {
+      const float* hr = T + (r - r0) * H;
+      float z0 = 0.f, z1 = 0.f;
+      for (int h = lane; h < H; h += 32) {
+        float a = hr[h];
+        z0 = fmaf(a, sW[h], z0);
+        if (nout == 2) z1 = fmaf(a, sW[H + h], z1);
+      }
+      z0 = warp_sum(z0);
+      if (nout == 2) z1 = warp_sum(z1);
+      if (lane == 0) {
+        const bool seg0 = r < p.rows0;
+        const bool valid = seg0 ? (r < nv0) : true;
+        const float t = seg0 ? p.target0 : p.target1;
+        const float wgt = valid ? p.scale / (float)(seg0 ? nv0 : n1) : 0.f;
+        z0 += sb[0];
+        if (nout == 2) z1 += sb[1];
+        float loss = 0.f, d0 = 0.f, d1 = 0.f;
+        if (p.loss_kind == CGL_LOSS_CE) {
+          float mx = fmaxf(z0, z1);
+          float lse = mx + logf(expf(z0 - mx) + expf(z1 - mx));
+          int cls = (int)t;
+          loss = lse - (cls == 0 ? z0 : z1);
+          float s0 = expf(z0 - lse), s1 = expf(z1 - lse);
+          d0 = (s0 - (cls == 0 ? 1.f : 0.f)) * wgt;
+          d1 = (s1 - (cls == 1 ? 1.f : 0.f)) * wgt;
+        } else {
+          float o = act_fwd(z0, p.last_act, p.slope);
+          float dlo;
+          if (p.loss_kind == CGL_LOSS_BCE) {
+            float lo = fmaxf(logf(o), -100.f);
+            float l1o = fmaxf(logf(1.f - o), -100.f);
+            loss = -(t * lo + (1.f - t) * l1o);
+            dlo = (o - t) / fmaxf((1.f - o) * o, 1e-12f);
+          } else {
+            float d = o - t;
+            loss = d * d;
+            dlo = 2.f * d;
+          }
+          d0 = dlo * wgt * act_bwd_from_out(o, p.last_act, p.slope);
+        }
+        if (!valid) { d0 = 0.f; d1 = 0.f; }
+        sloss[r] = valid ? loss : 0.f;
+        sdz[r * nout] = d0;
+        if (nout == 2) sdz[r * nout + 1] = d1;
+      }
+    }
+    __syncthreads();
+
+    // ---- dZ of the last hidden layer for the chunk: (dlogits . W) * act'(h), four consecutive h per thread ----
+    for (int i = tid; i < nr * (H >> 2); i += HEAD_THREADS) {
+      const int rl = i / (H >> 2), h = 4 * (i - rl * (H >> 2));
+      const int r = r0 + rl;
+      const float4 a4 = *reinterpret_cast<const float4*>(T + rl * H + h);
+      const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+      float ov[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float v = sdz[r * nout] * sW[h + e];
+        if (nout == 2) v = fmaf(sdz[r * nout + 1], sW[H + h + e], v);
+        ov[e] = v * act_bwd_from_out(av[e], p.hidden_act, p.slope);
+      }
+      *reinterpret_cast<float4*>(dz + (long long)r * H + h) = make_float4(ov[0], ov[1], ov[2], ov[3]);
+    }
+
+    // ---- weight gradient of the last layer, rows ascending (continued over the chunks) ----
+    if (p.train) {
+#pragma unroll
+      for (int j = 0; j < HEAD_MAXJ; ++j) {
+        const int h = tid + j * HEAD_THREADS;
+        if (h < H) {
+          for (int rl = 0; rl < nr; ++rl) {
+            const float a = T[rl * H + h];
+            g0[j] = fmaf(sdz[(r0 + rl) * nout], a, g0[j]);
+            if (nout == 2) g1[j] = fmaf(sdz[(r0 + rl) * nout + 1], a, g1[j]);
+          }
+        }
+      }
+    }
+    __syncthreads();                         // the tile is overwritten by the chunk requested in the next iteration
+  }
+
+  if (tid == 0) {
+    float l0 = 0.f, l1 = 0.f;
+    for (int r = 0; r < p.rows0; ++r) l0 += sloss[r];
+    for (int r = p.rows0; r < p.rows; ++r) l1 += sloss[r];
+    float tot = 0.f;
+    if (nv0 > 0) tot += l0 / (float)nv0;
+    if (n1 > 0) tot += l1 / (float)n1;
+    p.out_loss[g] = tot * p.scale;
+  }
+
+  if (p.train) {
+    const AdamScalars s = p.scal ? p.scal[g] : make_adam_scalars(p.step[rowid], p.lr, p.b1, p.b2, p.eps);
+    float* Mo = p.adam_m + (long long)rowid * p.ldp;
+    float* Vo = p.adam_v + (long long)rowid * p.ldp;
+#pragma unroll
+    for (int j = 0; j < HEAD_MAXJ; ++j) {
+      const int h = tid + j * HEAD_THREADS;
+      if (h < H) {
+        {
+          long long o = p.w_off + h;
+          float w = sW[h], mm = Mo[o], vv = Vo[o];
+          adam_update(w, mm, vv, g0[j], s);
+          W[h] = w; Mo[o] = mm; Vo[o] = vv;
+        }
+        if (nout == 2) {
+          long long o = p.w_off + H + h;
+          float w = sW[H + h], mm = Mo[o], vv = Vo[o];
+          adam_update(w, mm, vv, g1[j], s);
+          W[H + h] = w; Mo[o] = mm; Vo[o] = vv;
+        }
+      }
+    }
+    if (tid < nout) {
+      float gb = 0.f;
+      for (int r = 0; r < p.rows; ++r) gb += sdz[r * nout + tid];
+      long long o = p.b_off + tid;
+      float w = sb[tid], mm = Mo[o], vv = Vo[o];
+      adam_update(w, mm, vv, gb, s);
+      Bv[tid] = w; Mo[o] = mm; Vo[o] = vv;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 static int validate_d_arch(const cgl_mlp_desc* a, int loss_kind) {
   CGL_REQUIRE(a != nullptr, "arch is NULL");
@@ -269,11 +456,19 @@ static int launch_head(const cgl_mlp_desc* a, const cgl_mlp_layout& lay, int G, 
   h.target0 = t0; h.target1 = t1; h.scale = scale;
   h.out_loss = out_loss; h.train = train;
   size_t smem = (size_t)(h.nout * h.H + rows * h.nout + rows + h.nout) * sizeof(float);
-  if (smem > 48 * 1024) {
-    CGL_CHECK_CUDA(cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  }
+  const size_t smem_stream = smem + (size_t)2 * HEAD_CH * h.H * sizeof(float);
+  const bool stream_ok = h.H % 4 == 0 && h.H <= HEAD_MAXJ * HEAD_THREADS && aligned16(h.hin) && aligned16(h.dz) &&
+                         h.hin_gstride % 4 == 0 && h.dz_gstride % 4 == 0 && smem_stream <= 200 * 1024;
   ProfScope prof(CGL_PROF_HEAD, 8.0 * G * rows * (double)h.H, 0.0, st);   // last hidden read, its gradient written
-  head_kernel<<<G, HEAD_THREADS, smem, st>>>(h);
+  if (stream_ok) {
+    CGL_CHECK_CUDA(cudaFuncSetAttribute(head_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_stream));
+    head_stream_kernel<<<G, HEAD_THREADS, smem_stream, st>>>(h);
+  } else {
+    if (smem > 48 * 1024) {
+      CGL_CHECK_CUDA(cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    head_kernel<<<G, HEAD_THREADS, smem, st>>>(h);
+  }
   CGL_CHECK_LAUNCH();
   return CGL_OK;
 }
