@@ -42,7 +42,6 @@ constexpr int TC_MMA_WARP = 8;          // warp 8: TMEM allocation and the singl
 constexpr int TC_THREADS = TC_LOADER_THREADS + 32;
 constexpr int TC_MAX_BN = 256;
 constexpr int TC_TUNE_DEFAULT = 1 | 8 | 32;
-constexpr int TC_PF_DIST = 256, TC_PF_CHUNK = 256;   // operand L2 prefetch: distance and chunk, in floats of K
 constexpr uint32_t TC_WAIT_HINT_NS = 20000u;
 
 // ---- PTX wrappers ----------------------------------------------------------------------------
@@ -238,9 +237,8 @@ struct TcParams {
   const float* saved; long long saved_gstride;  // EPI_BWD_DATA: saved[g] + n*ldc + m
   float* adam_m; float* adam_v; const int* step; float lr, b1, b2, eps;  // EPI_ADAM
   const AdamScalars* scal;  // EPI_ADAM: [G] precomputed scalars of this step (NULL: derive from step)
-  int tune;  // bits (tc_tune()): 1 = L2 prefetch of the Adam tile under the main loop, 2 / 4 = L2 prefetch of the A / B
-             // operand, 8 / 16 = persistent kernel (tc_persist.cuh) for the data-gradient / forward product,
-             // 32 / 64 = 16 loader warps in the one-tile forward / data-gradient kernel
+  int tune;  // bits (tc_tune()): 1 = L2 prefetch of the Adam tile under the main loop, 8 / 16 = persistent kernel
+             // (tc_persist.cuh) for the data-gradient / forward product, 32 = 16 loader warps in the one-tile forward kernel
 };
 
 // TMEM plan (512 columns, 1 CTA per SM). The tensor core TRUNCATES when it adds into an fp32
@@ -373,7 +371,11 @@ __global__ void __launch_bounds__(LW * 32 + 32, OCC) tc_grouped_gemm_kernel(cons
     // ===== loader warps: global -> registers (several k-blocks in flight) -> split -> shared =====
     const Rows RA = resolve(p.A, g);
     const Rows RB = resolve(p.B, g);
-    const int npb = bn_pad >> 2;  // patches of the B tile (K-major tiles beyond bn are zero-filled)
+    // patches of the B tile that hold data. K-major B (lines = batch rows): the lines beyond N are neither loaded nor
+    // stored -- whatever the stage holds there only reaches accumulator columns n >= N, which the epilogue never
+    // reads (for a batch of 100 in a 112-wide tile that is 7 of 32 patches of STS traffic on the L1TEX pipe).
+    const int b_lines = (p.N - n0 < bn) ? (p.N - n0) : bn;
+    const int npb = B_KMAJOR ? ((b_lines + 3) >> 2) : (bn_pad >> 2);
     constexpr int DEPTH = (LW == 16) ? 4 : ((NB == 4 && OCC == 1) ? 3 : 2);  // k-blocks of global loads in flight per thread
     float4 ra[DEPTH][NA], rb[DEPTH][NBW];
     auto load_block = [&](int kb, float4 (&qa)[NA], float4 (&qb)[NBW]) {
@@ -429,34 +431,6 @@ __global__ void __launch_bounds__(LW * 32 + 32, OCC) tc_grouped_gemm_kernel(cons
     };
     const int kb_prefetch = nkb > DEPTH ? nkb - DEPTH - 1 : 0;   // right after the last operand loads are issued
 
-    // Operand prefetch HBM -> L2, TC_PF_DIST..TC_PF_DIST+TC_PF_CHUNK floats of K ahead of the register loads: the
-    // weights are read exactly once, so every register load of W would otherwise pay the full HBM latency, and
-    // with 2-3 k-blocks in flight per thread (all the registers allow) the k-block time is latency / depth.
-    int pf_k = DEPTH * TC_BK;     // first k not yet requested by anyone
-    auto operand_prefetch = [&](int k_now) {
-      if (!(p.tune & 6) || pf_k >= p.K || k_now + TC_PF_DIST < pf_k) return;
-      const int k1 = (pf_k + TC_PF_CHUNK < p.K) ? pf_k + TC_PF_CHUNK : p.K;
-      if (p.tune & 2) {
-        if (A_KMAJOR) {   // 128 rows (m), each [pf_k, k1) contiguous
-          const int r = m0 + tid;
-          if (tid < TC_BM && r < p.M) l2_prefetch_bulk(row_ptr(RA, r) + pf_k, (uint32_t)(k1 - pf_k) * 4u);
-        } else {          // rows are k, each [m0, m0 + 128) contiguous
-          const uint32_t mb = (uint32_t)(((p.M - m0 < TC_BM) ? (p.M - m0) : TC_BM) * 4);
-          for (int k = pf_k + tid; k < k1; k += LT) l2_prefetch_bulk(row_ptr(RA, k) + m0, mb);
-        }
-      }
-      if (p.tune & 4) {
-        if (B_KMAJOR) {
-          const int r = n0 + tid;
-          if (tid < bn && r < p.N) l2_prefetch_bulk(row_ptr(RB, r) + pf_k, (uint32_t)(k1 - pf_k) * 4u);
-        } else {
-          const int nb4 = ((p.N - n0 < bn) ? (p.N - n0) : bn) * 4;
-          for (int k = pf_k + tid; k < k1; k += LT) l2_prefetch_bulk(row_ptr(RB, k) + n0, (uint32_t)nb4);
-        }
-      }
-      pf_k = k1;
-    };
-    operand_prefetch(0);
     for (int kb0 = 0; kb0 < nkb; kb0 += DEPTH) {
 #pragma unroll
       for (int d = 0; d < DEPTH; ++d) {
@@ -466,7 +440,6 @@ __global__ void __launch_bounds__(LW * 32 + 32, OCC) tc_grouped_gemm_kernel(cons
           if (kb == 0 && warp == 0) TC_STAMP(3);
           if (kb + DEPTH < nkb) load_block(kb + DEPTH, ra[d], rb[d]);
           if (kb == kb_prefetch) adam_tile_prefetch();
-          operand_prefetch((kb + 1) * TC_BK);
         }
       }
     }
@@ -756,7 +729,6 @@ static inline cudaError_t launch_tc_gemm(TcParams p, int G, cudaStream_t stream)
   p.n_main = tc_n_main(p.bn);
   p.tmem_cols = TC_TMEM_COLS;
   if (p.bn <= 128 && EPI == EPI_FWD && (p.tune & 32)) return launch_tc_gemm_nb<A_KMAJOR, B_KMAJOR, EPI_FWD, 4, 1, 16>(p, G, stream);
-  if (p.bn <= 128 && !A_KMAJOR && B_KMAJOR && (p.tune & 64)) return launch_tc_gemm_nb<A_KMAJOR, B_KMAJOR, EPI, 4, 1, 16>(p, G, stream);
   if (p.bn <= 128) return launch_tc_gemm_nb<A_KMAJOR, B_KMAJOR, EPI, 4, 1>(p, G, stream);
   return launch_tc_gemm_nb<A_KMAJOR, B_KMAJOR, EPI, 8, 1>(p, G, stream);
 }

@@ -142,10 +142,12 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_persistent_gemm_kernel(cons
         }
       }
     };
+    int ld_kb = 0, ld_tile = 0;
     auto load_block = [&](int j, float4 (&qa)[4], float4 (&qb)[NB]) {
-      const int i = j / nkb;
-      const int kb = j - i * nkb;
-      if (kb == 0) setup_tile(i);   // loads are issued in increasing j: exactly once per tile
+      (void)j;                      // loads are issued in increasing j: counters instead of a division per k-block
+      const int kb = ld_kb;
+      if (kb == 0) setup_tile(ld_tile);
+      if (++ld_kb == nkb) { ld_kb = 0; ++ld_tile; }
       const int k0 = kb * TC_BK;
       const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
       if (A_KMAJOR) {
@@ -172,6 +174,15 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_persistent_gemm_kernel(cons
     int st_s = 0;
     uint32_t st_par = 1;
     bool st_first = true;
+    int st_kb = 0, st_tile = 0;
+    int npb_st = npb;   // B patches of the tile being STORED that hold data (K-major B: lines beyond N are skipped, see tc_gemm.cuh)
+    auto store_tile_setup = [&](int i) {
+      if (!B_KMAJOR) return;
+      int g, m0s, n0s;
+      tile_coords(i, g, m0s, n0s);
+      const int lines = (p.N - n0s < bn) ? (p.N - n0s) : bn;
+      npb_st = (lines + 3) >> 2;
+    };
     auto store_block = [&](const float4 (&qa)[4], const float4 (&qb)[NB]) {
       if (!st_first) mbar_wait(smem_u32(&bar_empty[st_s]), st_par);
       char* a_hi = smem + (size_t)st_s * stage_bytes;
@@ -183,7 +194,7 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_persistent_gemm_kernel(cons
 #pragma unroll
       for (int u = 0; u < NB; ++u) {
         const int pp = warp + 8 * u;
-        if (pp < npb) tc_split_store(b_hi, b_lo, tc_patch_offset<B_KMAJOR>(pp, lane), qb[u]);
+        if (pp < npb_st) tc_split_store(b_hi, b_lo, tc_patch_offset<B_KMAJOR>(pp, lane), qb[u]);
       }
       fence_proxy_async_smem();
       mbar_arrive(smem_u32(&bar_full[st_s]));
@@ -200,6 +211,8 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_persistent_gemm_kernel(cons
       for (int d = 0; d < DEPTH; ++d) {
         const int j = j0 + d;
         if (j < total) {
+          if (st_kb == 0) store_tile_setup(st_tile);      // (no division in this loop: it is issue-bound)
+          if (++st_kb == nkb) { st_kb = 0; ++st_tile; }
           store_block(ra[d], rb[d]);
           if (j + DEPTH < total) load_block(j + DEPTH, ra[d], rb[d]);
         }
