@@ -31,7 +31,7 @@ def classify(name):
         return ("linear_bwd_data" if tc_bwd else "linear_wgrad") + tag, True
     if "bias_grad_kernel<(bool)1>" in name or "bias_grad_kernel<1>" in name:
         return "linear_wgrad+adam[tcgen05]", False      # rides with the weight-gradient launch
-    for key, cls in (("head_kernel", "head_loss"), ("bn_fwd_kernel", "batchnorm_fwd"), ("bn_bwd_kernel", "batchnorm_bwd"),
+    for key, cls in (("head_kernel", "head_loss"), ("head_stream_kernel", "head_loss"), ("bn_fwd_kernel", "batchnorm_fwd"), ("bn_bwd_kernel", "batchnorm_bwd"),
                      ("bn_fwd_smem_kernel", "batchnorm_fwd"), ("bn_bwd_smem_kernel", "batchnorm_bwd"),
                      ("wsum_kernel", "mix/aggregate"), ("bcast_mix_kernel", "mix/aggregate"),
                      ("mix_csr_kernel", "mix/aggregate"), ("dxg_reduce_kernel", "mix/aggregate"),
