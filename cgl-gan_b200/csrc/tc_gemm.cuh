@@ -40,6 +40,9 @@ constexpr int TC_MAX_STAGES = 4;
 constexpr int TC_LOADER_THREADS = 256;  // warps 0..7: operand staging, then the epilogue
 constexpr int TC_MMA_WARP = 8;          // warp 8: TMEM allocation and the single MMA-issuing thread
 constexpr int TC_THREADS = TC_LOADER_THREADS + 32;
+#ifndef TC_LW16_DEPTH
+#define TC_LW16_DEPTH 3   // k-blocks of loads in flight per thread of the 16-loader-warp forward kernel
+#endif
 constexpr int TC_MAX_BN = 256;
 constexpr int TC_TUNE_DEFAULT = 1 | 8 | 32;
 constexpr uint32_t TC_WAIT_HINT_NS = 20000u;
@@ -376,7 +379,7 @@ __global__ void __launch_bounds__(LW * 32 + 32, OCC) tc_grouped_gemm_kernel(cons
     // reads (for a batch of 100 in a 112-wide tile that is 7 of 32 patches of STS traffic on the L1TEX pipe).
     const int b_lines = (p.N - n0 < bn) ? (p.N - n0) : bn;
     const int npb = B_KMAJOR ? ((b_lines + 3) >> 2) : (bn_pad >> 2);
-    constexpr int DEPTH = (LW == 16) ? 4 : ((NB == 4 && OCC == 1) ? 3 : 2);  // k-blocks of global loads in flight per thread
+    constexpr int DEPTH = (LW == 16) ? TC_LW16_DEPTH : ((NB == 4 && OCC == 1) ? 3 : 2);  // k-blocks of global loads in flight per thread
     float4 ra[DEPTH][NA], rb[DEPTH][NBW];
     auto load_block = [&](int kb, float4 (&qa)[NA], float4 (&qb)[NBW]) {
       const int k0 = kb * TC_BK;
