@@ -40,11 +40,17 @@ constexpr int TC_MAX_STAGES = 4;
 constexpr int TC_LOADER_THREADS = 256;  // warps 0..7: operand staging, then the epilogue
 constexpr int TC_MMA_WARP = 8;          // warp 8: TMEM allocation and the single MMA-issuing thread
 constexpr int TC_THREADS = TC_LOADER_THREADS + 32;
+#ifndef TC_WG_DEPTH
+#define TC_WG_DEPTH 3    // 16-row k-blocks of loads in flight per thread of the weight-gradient kernel
+#endif
+#ifndef TC_WG_STAGES
+#define TC_WG_STAGES 2   // its 32 KB stages (the Adam epilogue's transpose buffer needs 64 KB)
+#endif
 #ifndef TC_LW16_DEPTH
 #define TC_LW16_DEPTH 3   // k-blocks of loads in flight per thread of the 16-loader-warp forward kernel
 #endif
 constexpr int TC_MAX_BN = 256;
-constexpr int TC_TUNE_DEFAULT = 1 | 8 | 32;
+constexpr int TC_TUNE_DEFAULT = 1 | 8 | 32 | 64;
 constexpr uint32_t TC_WAIT_HINT_NS = 20000u;
 
 // ---- PTX wrappers ----------------------------------------------------------------------------
@@ -183,28 +189,33 @@ __host__ __device__ inline uint32_t umma_idesc_tf32(bool a_mn_major, bool b_mn_m
 //       byte(t, k) = (t/32)*4096 + (k/4)*512 + (k%4)*128 + ((((t%32)/8) ^ (k%4)) * 32) + (t%8)*4
 //       LBO = 4096 (next 32 t), SBO = 512 (next 4 k); one MMA (8 k) = 2 atoms = 1024 B further
 //       patch p = 4 k x 32 t: k group p%8, t group p/8;  lane -> (k = 4*(p%8) + lane/8, t = 32*(p/8) + 4*(lane%8))
-template <bool KMAJOR>
+// BKT = K extent of a staged k-block: 32, or 16 for MN-major operands only (KG = BKT / 4 groups of 4 k-rows per 32 lines;
+// the K-major layout is tied to 32: one 128-byte swizzle row)
+template <bool KMAJOR, int BKT = 32>
 __device__ __forceinline__ float4 tc_patch_load(const Rows& R, int p, int lane, int t0, int dimT, int k0, int dimK) {
+  static_assert(BKT == 32 || (!KMAJOR && BKT == 16), "unsupported k-block");
+  constexpr int KG = BKT / 4;
   float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
   if (KMAJOR) {
     const int t = t0 + 4 * p + (lane >> 3);
     const int k = k0 + 4 * (lane & 7);
     if (t < dimT && k < dimK) v = __ldg(reinterpret_cast<const float4*>(row_ptr(R, t) + k));
   } else {
-    const int k = k0 + 4 * (p & 7) + (lane >> 3);
-    const int t = t0 + 32 * (p >> 3) + 4 * (lane & 7);
+    const int k = k0 + 4 * (p % KG) + (lane >> 3);
+    const int t = t0 + 32 * (p / KG) + 4 * (lane & 7);
     if (k < dimK && t < dimT) v = __ldg(reinterpret_cast<const float4*>(row_ptr(R, k) + t));
   }
   return v;
 }
-template <bool KMAJOR>
+template <bool KMAJOR, int BKT = 32>
 __device__ __forceinline__ uint32_t tc_patch_offset(int p, int lane) {
+  constexpr int KG = BKT / 4;
   if (KMAJOR) {
     const int r = 4 * p + (lane >> 3);
     return (uint32_t)(r * 128 + (((lane & 7) ^ (r & 7)) << 4));
   }
   const int kr = lane >> 3, c16 = lane & 7;
-  return (uint32_t)((p >> 3) * 4096 + (p & 7) * 512 + kr * 128 + (((c16 >> 1) ^ kr) << 5) + (c16 & 1) * 16);
+  return (uint32_t)((p / KG) * (KG * 512) + (p % KG) * 512 + kr * 128 + (((c16 >> 1) ^ kr) << 5) + (c16 & 1) * 16);
 }
 __device__ __forceinline__ void tc_split_store(char* hi, char* lo, uint32_t off, const float4& v) {
   // lo = x - hi is exact in fp32 (|lo| <= 2^-11 |x|, either sign); the tensor core drops its low 13 bits,
@@ -241,7 +252,8 @@ struct TcParams {
   float* adam_m; float* adam_v; const int* step; float lr, b1, b2, eps;  // EPI_ADAM
   const AdamScalars* scal;  // EPI_ADAM: [G] precomputed scalars of this step (NULL: derive from step)
   int tune;  // bits (tc_tune()): 1 = L2 prefetch of the Adam tile under the main loop, 8 / 16 = persistent kernel
-             // (tc_persist.cuh) for the data-gradient / forward product, 32 = 16 loader warps in the one-tile forward kernel
+             // (tc_persist.cuh) for the data-gradient / forward product, 32 = 16 loader warps in the one-tile forward kernel,
+             // 64 = 16-row stages (two of them) in the weight-gradient kernel
 };
 
 // TMEM plan (512 columns, 1 CTA per SM). The tensor core TRUNCATES when it adds into an fp32
@@ -266,12 +278,15 @@ __host__ __device__ inline int tc_n_main(int bn) {
 // registers) lets one CTA's HBM-bound Adam epilogue run under another CTA's main loop.
 // LW = loader warps (8, or 16 for the long-K one-CTA-per-SM variants: the loader loop is ~330 instructions per
 // k-block at ~0.35 IPC per scheduler with two warps each, so four warps per scheduler hide more of its latency)
-template <bool A_KMAJOR, bool B_KMAJOR, int EPI, int NB, int OCC, int LW>
+// BKT = K extent of a stage (32; 16 for the two-CTAs-per-SM weight-gradient variant: two 32 KB stages instead of one
+// of 64 KB, so a store overlaps the MMAs of the previous k-block, and 16 registers of loads per k-block instead of 32)
+template <bool A_KMAJOR, bool B_KMAJOR, int EPI, int NB, int OCC, int LW, int BKT>
 __global__ void __launch_bounds__(LW * 32 + 32, OCC) tc_grouped_gemm_kernel(const TcParams p) {
   constexpr int LT = LW * 32;          // loader (= epilogue) threads
   constexpr int MMAW = LW;             // the warp after them allocates TMEM and issues the MMAs
-  constexpr int NA = 32 / LW;          // A patches per loader warp (a 128-line tile has 32)
-  constexpr int NBW = NB * 8 / LW;     // B patches per loader warp
+  constexpr int KG = BKT / 4;          // groups of 4 k-rows per k-block
+  constexpr int NA = 4 * KG / LW;      // A patches per loader warp (a 128-line tile has 4 * KG)
+  constexpr int NBW = NB * KG / LW;    // B patches per loader warp
   extern __shared__ __align__(1024) char tc_smem[];
   __shared__ __align__(8) unsigned long long bar_full[TC_MAX_STAGES];
   __shared__ __align__(8) unsigned long long bar_empty[TC_MAX_STAGES];
@@ -287,9 +302,9 @@ __global__ void __launch_bounds__(LW * 32 + 32, OCC) tc_grouped_gemm_kernel(cons
   if (warp == 0) TC_STAMP(0);
 
   // stage layout: [A hi | A lo | B hi | B lo]
-  const uint32_t a_bytes = TC_BM * TC_BK * 4;
+  const uint32_t a_bytes = TC_BM * BKT * 4;
   const int bn_pad = (bn + 31) & ~31;  // MN-major staging works in groups of 32 lines
-  const uint32_t b_bytes = (uint32_t)bn_pad * TC_BK * 4;
+  const uint32_t b_bytes = (uint32_t)bn_pad * BKT * 4;
   const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
   // the swizzled layout XORs absolute address bits [7,9) into [5,7): every buffer starts 1024-aligned
   char* smem = tc_smem + ((1024u - (smem_u32(tc_smem) & 1023u)) & 1023u);
@@ -297,7 +312,7 @@ __global__ void __launch_bounds__(LW * 32 + 32, OCC) tc_grouped_gemm_kernel(cons
   const int stride = tc_region_stride(bn);
   const int n_main = p.n_main;
   const uint32_t tmem_cols = (uint32_t)p.tmem_cols;
-  const int nkb = (p.K + TC_BK - 1) / TC_BK;
+  const int nkb = (p.K + BKT - 1) / BKT;
   const int nks = (p.K + 7) >> 3;  // k-steps of 8 that carry data
 
   if (tid == 0) {
@@ -321,8 +336,8 @@ __global__ void __launch_bounds__(LW * 32 + 32, OCC) tc_grouped_gemm_kernel(cons
       const uint32_t idesc = umma_idesc_tf32(!A_KMAJOR, !B_KMAJOR, bn);
       // K-major : SWIZZLE_128B, SBO = 1024 (next 8 lines), LBO unused, a k-step of 8 = 32 B inside the span
       // MN-major: SWIZZLE_128B_BASE32B, LBO = 4096 (next 32 lines), SBO = 512 (next 4 k), a k-step of 8 = 1024 B
-      const uint32_t a_lbo = A_KMAJOR ? 16u : 4096u, a_sbo = A_KMAJOR ? 1024u : 512u;
-      const uint32_t b_lbo = B_KMAJOR ? 16u : 4096u, b_sbo = B_KMAJOR ? 1024u : 512u;
+      const uint32_t a_lbo = A_KMAJOR ? 16u : (uint32_t)(KG * 512), a_sbo = A_KMAJOR ? 1024u : 512u;
+      const uint32_t b_lbo = B_KMAJOR ? 16u : (uint32_t)(KG * 512), b_sbo = B_KMAJOR ? 1024u : 512u;
       const uint32_t a_step = A_KMAJOR ? 32u : 1024u, b_step = B_KMAJOR ? 32u : 1024u;
       const uint32_t a_lay = A_KMAJOR ? UMMA_LAYOUT_SW128 : UMMA_LAYOUT_SW128_BASE32B;
       const uint32_t b_lay = B_KMAJOR ? UMMA_LAYOUT_SW128 : UMMA_LAYOUT_SW128_BASE32B;
@@ -335,7 +350,7 @@ __global__ void __launch_bounds__(LW * 32 + 32, OCC) tc_grouped_gemm_kernel(cons
         const uint32_t sa_hi = smem_u32(smem + (size_t)s * stage_bytes);
         const uint32_t sa_lo = sa_hi + a_bytes, sb_hi = sa_hi + 2 * a_bytes, sb_lo = sb_hi + b_bytes;
 #pragma unroll
-        for (int j = 0; j < TC_BK / 8; ++j) {
+        for (int j = 0; j < BKT / 8; ++j) {
           if (ks < nks) {
             const uint64_t dah = umma_desc(sa_hi + j * a_step, a_lbo, a_sbo, a_lay);
             const uint64_t dal = umma_desc(sa_lo + j * a_step, a_lbo, a_sbo, a_lay);
@@ -378,17 +393,17 @@ __global__ void __launch_bounds__(LW * 32 + 32, OCC) tc_grouped_gemm_kernel(cons
     // stored -- whatever the stage holds there only reaches accumulator columns n >= N, which the epilogue never
     // reads (for a batch of 100 in a 112-wide tile that is 7 of 32 patches of STS traffic on the L1TEX pipe).
     const int b_lines = (p.N - n0 < bn) ? (p.N - n0) : bn;
-    const int npb = B_KMAJOR ? ((b_lines + 3) >> 2) : (bn_pad >> 2);
-    constexpr int DEPTH = (LW == 16) ? TC_LW16_DEPTH : ((NB == 4 && OCC == 1) ? 3 : 2);  // k-blocks of global loads in flight per thread
+    const int npb = B_KMAJOR ? ((b_lines + 3) >> 2) : (bn_pad >> 5) * KG;
+    constexpr int DEPTH = (LW == 16) ? TC_LW16_DEPTH : (BKT == 16 ? TC_WG_DEPTH : ((NB == 4 && OCC == 1) ? 3 : 2));  // k-blocks of global loads in flight per thread
     float4 ra[DEPTH][NA], rb[DEPTH][NBW];
     auto load_block = [&](int kb, float4 (&qa)[NA], float4 (&qb)[NBW]) {
-      const int k0 = kb * TC_BK;
+      const int k0 = kb * BKT;
 #pragma unroll
-      for (int i = 0; i < NA; ++i) qa[i] = tc_patch_load<A_KMAJOR>(RA, warp + LW * i, lane, m0, p.M, k0, p.K);
+      for (int i = 0; i < NA; ++i) qa[i] = tc_patch_load<A_KMAJOR, BKT>(RA, warp + LW * i, lane, m0, p.M, k0, p.K);
 #pragma unroll
       for (int i = 0; i < NBW; ++i) {
         const int pp = warp + LW * i;
-        qb[i] = (pp < npb) ? tc_patch_load<B_KMAJOR>(RB, pp, lane, n0, p.N, k0, p.K) : make_float4(0.f, 0.f, 0.f, 0.f);
+        qb[i] = (pp < npb) ? tc_patch_load<B_KMAJOR, BKT>(RB, pp, lane, n0, p.N, k0, p.K) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
     int st_s = 0;            // stage of the next store
@@ -401,11 +416,11 @@ __global__ void __launch_bounds__(LW * 32 + 32, OCC) tc_grouped_gemm_kernel(cons
       char* b_hi = a_hi + 2 * a_bytes;
       char* b_lo = b_hi + b_bytes;
 #pragma unroll
-      for (int i = 0; i < NA; ++i) tc_split_store(a_hi, a_lo, tc_patch_offset<A_KMAJOR>(warp + LW * i, lane), qa[i]);
+      for (int i = 0; i < NA; ++i) tc_split_store(a_hi, a_lo, tc_patch_offset<A_KMAJOR, BKT>(warp + LW * i, lane), qa[i]);
 #pragma unroll
       for (int i = 0; i < NBW; ++i) {
         const int pp = warp + LW * i;
-        if (pp < npb) tc_split_store(b_hi, b_lo, tc_patch_offset<B_KMAJOR>(pp, lane), qb[i]);
+        if (pp < npb) tc_split_store(b_hi, b_lo, tc_patch_offset<B_KMAJOR, BKT>(pp, lane), qb[i]);
       }
       fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core (async proxy)
       mbar_arrive(smem_u32(&bar_full[st_s]));
@@ -686,18 +701,18 @@ static inline int tc_pow2_cols(int cols) {
   return c;
 }
 
-template <bool A_KMAJOR, bool B_KMAJOR, int EPI, int NB, int OCC, int LW = 8>
+template <bool A_KMAJOR, bool B_KMAJOR, int EPI, int NB, int OCC, int LW = 8, int BKT = 32>
 static inline cudaError_t launch_tc_gemm_nb(const TcParams& p, int G, cudaStream_t stream) {
   static bool attr_set = false;  // per template instantiation
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tc_grouped_gemm_kernel<A_KMAJOR, B_KMAJOR, EPI, NB, OCC, LW>,
+    cudaError_t e = cudaFuncSetAttribute(tc_grouped_gemm_kernel<A_KMAJOR, B_KMAJOR, EPI, NB, OCC, LW, BKT>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BUDGET);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  const size_t smem = (size_t)p.n_stages * tc_stage_bytes(p.bn) + 1024;
+  const size_t smem = (size_t)p.n_stages * (tc_stage_bytes(p.bn) * BKT / TC_BK) + 1024;
   dim3 grid((p.N + p.bn - 1) / p.bn, (p.M + TC_BM - 1) / TC_BM, G);
-  tc_grouped_gemm_kernel<A_KMAJOR, B_KMAJOR, EPI, NB, OCC, LW><<<grid, LW * 32 + 32, smem, stream>>>(p);
+  tc_grouped_gemm_kernel<A_KMAJOR, B_KMAJOR, EPI, NB, OCC, LW, BKT><<<grid, LW * 32 + 32, smem, stream>>>(p);
   count_launch();
   return cudaGetLastError();
 }
@@ -717,15 +732,21 @@ static inline cudaError_t launch_tc_gemm(TcParams p, int G, cudaStream_t stream)
   if (G <= 0 || p.M <= 0 || p.N <= 0) return cudaSuccess;
   p.tune = tc_tune();
   const int nks = (p.K + 7) / 8;
-  if ((EPI == EPI_ADAM || EPI == EPI_STORE) && !A_KMAJOR && !B_KMAJOR && nks <= TC_MAX_ACCUM) {
+  if constexpr ((EPI == EPI_ADAM || EPI == EPI_STORE) && !A_KMAJOR && !B_KMAJOR) {
+   if (nks <= TC_MAX_ACCUM) {
     // short-K weight gradient: its epilogue (24 B per parameter for Adam) is the HBM-bound part of a round.
     // 128-wide tiles, one stage (64 KB) and 256 TMEM columns -> two CTAs per SM overlap epilogue and main loop.
     const int tiles = (p.N + 127) / 128;
     p.bn = ((p.N + tiles - 1) / tiles + 15) / 16 * 16;
-    p.n_stages = 1;
     p.n_main = 1;
     p.tmem_cols = tc_pow2_cols(2 * tc_region_stride(p.bn));
+    if (p.tune & 64) {   // two 32 KB stages of 16 k-rows
+      p.n_stages = TC_WG_STAGES;
+      return launch_tc_gemm_nb<A_KMAJOR, B_KMAJOR, EPI, 4, 2, 8, 16>(p, G, stream);
+    }
+    p.n_stages = 1;
     return launch_tc_gemm_nb<A_KMAJOR, B_KMAJOR, EPI, 4, 2>(p, G, stream);
+  }
   }
   p.bn = tc_pick_bn(p.N, p.K);
   p.n_stages = tc_pick_stages(p.bn);
