@@ -40,6 +40,9 @@ constexpr int TC_MAX_STAGES = 4;
 constexpr int TC_LOADER_THREADS = 256;  // warps 0..7: operand staging, then the epilogue
 constexpr int TC_MMA_WARP = 8;          // warp 8: TMEM allocation and the single MMA-issuing thread
 constexpr int TC_THREADS = TC_LOADER_THREADS + 32;
+#ifndef TC_WG_UNR
+#define TC_WG_UNR 3      // float4 triples (W, m, v) in flight per thread in the Adam epilogue of the weight-gradient kernel
+#endif
 #ifndef TC_WG_DEPTH
 #define TC_WG_DEPTH 3    // 16-row k-blocks of loads in flight per thread of the weight-gradient kernel
 #endif
@@ -532,7 +535,7 @@ __global__ void __launch_bounds__(LW * 32 + 32, OCC) tc_grouped_gemm_kernel(cons
       const int n_valid = (p.N - n0 < bn) ? (p.N - n0) : bn;
       const int m4_valid = ((p.M - m0 < TC_BM) ? (p.M - m0) : TC_BM) >> 2;   // M % 4 == 0 (MN-major A operand)
       const int items = n_valid * (TC_BM / 4);
-      constexpr int UNR = (OCC == 2) ? 3 : 4;
+      constexpr int UNR = (OCC == 2) ? TC_WG_UNR : 4;
       for (int i0 = tid; i0 < items; i0 += LT * UNR) {
         float4 w4[UNR], a4[UNR], v4[UNR];
         long long off[UNR];
