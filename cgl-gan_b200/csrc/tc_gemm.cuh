@@ -20,13 +20,18 @@
 // conflict-free) instead of by TMA; ragged / concatenated / index-selected row sources
 // (RowMap) come for free.
 //
-// Pipeline per CTA (128 x BN output tile, BK = 32, 2..4 shared-memory stages, no CTA-wide barrier in the loop):
-//   warps 0..7 : LDG (two k-blocks in flight per thread) -> split -> STS stage s -> fence.proxy.async
-//                -> mbarrier arrive full[s]; wait empty[s] before a stage is overwritten
-//   warp 8     : one thread waits full[s], issues 12 tcgen05.mma (4 k-steps x 3 split products),
-//                tcgen05.commit -> empty[s]; a last commit -> done
-//   epilogue   : warps 0..7 wait done, tcgen05.ld 32x32b.x16 of every region, fused bias+activation /
-//                activation derivative / Adam, coalesced stores.
+// Pipeline per CTA (128 x BN output tile, k-blocks of BKT = 32 (16) rows, 2..4 shared-memory stages, no CTA-wide
+// barrier in the loop):
+//   LW loader warps : LDG (2..3 k-blocks in flight per thread) -> split -> STS stage s -> fence.proxy.async
+//                     -> mbarrier arrive full[s]; wait empty[s] before a stage is overwritten
+//   next warp       : one thread waits full[s], issues 3 tcgen05.mma per k-step of 8 (the split products),
+//                     tcgen05.commit -> empty[s]; a last commit -> done
+//   epilogue        : the loader warps wait done, tcgen05.ld 32x32b.x16 of every region, fused bias+activation /
+//                     activation derivative / Adam, coalesced stores.
+// Variants in use (launch_tc_gemm, linear.cuh):
+//   forward        : LW = 16, one CTA per SM, 3 stages            (the loader loop is the limiter: 4 warps per scheduler)
+//   data gradient  : tc_persist.cuh (persistent, dedicated epilogue warps); batch tiles wider than 128: LW = 8 here
+//   weight gradient: OCC = 2 (two CTAs per SM), BKT = 16, two 32 KB stages, fused Adam epilogue
 #pragma once
 #include <stdlib.h>
 
