@@ -39,7 +39,7 @@ def parse():
     ap.add_argument("--clients", type=int, default=1024, help="clients per GPU")
     ap.add_argument("--clients-per-server", type=int, default=4)
     ap.add_argument("--dataset", default="mnist", choices=["mnist", "2dmg"])
-    ap.add_argument("--algo", default="cglgan")
+    ap.add_argument("--algo", default="cglgan", help="cglgan | capgan | mixed | mdgan | acgan (MD-style round) | flgan (FL-style step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-clients", type=int, default=16)
     return ap.parse_args()
@@ -47,6 +47,15 @@ def parse():
 
 def workload_config(args, world):
     shape = (1, 28, 28) if args.dataset == "mnist" else (2,)
+    if args.algo == "flgan":
+        return {
+            "workload": f"FLGAN {args.dataset.upper()} step: {args.clients} clients/GPU, one local minibatch (D step + G step, "
+                        f"batch 100) on every client, then the FedAvg of all G and D (FLGAN/MNIST/flgan.py:143-163,245-270)",
+            "algo": "flgan", "dataset": f"synthetic {args.dataset}-shaped tanh(N(0,1))", "img_shape": list(shape),
+            "num_workers": args.clients * world, "num_servers": 1, "batch_size": 100,
+            "parallelism": f"clients sharded x{world}",
+            "l2_policy": "inputs larger than L2 (>= 6 GB of per-client state streamed per step), no explicit flush",
+        }
     return {
         "workload": f"{args.algo.upper()} {args.dataset.upper()} round: {args.clients} clients/GPU, "
                     f"{args.clients // args.clients_per_server} servers/GPU, batch 100, epoch 1, cloud_epoch 1, iid 1",
@@ -69,6 +78,23 @@ def cpu_round_rate(args, sample_clients, rounds, warmup):
     per = args.clients_per_server
     W, S, B = sample_clients, sample_clients // per, 100
     torch.manual_seed(20211212)
+    if args.algo == "flgan":
+        from oracle.rounds import OracleFL
+        orc = OracleFL(W, B, shape)
+        orc.load_global()
+        g = torch.Generator().manual_seed(1)
+        real = torch.tanh(torch.randn(W, B, d, generator=g))
+        n_real = torch.full((W,), B, dtype=torch.int32)
+        times = []
+        for r in range(warmup + rounds):
+            z_d, z_g = torch.randn(W, B, 100, generator=g), torch.randn(W, B, 100, generator=g)
+            t0 = time.perf_counter()
+            orc.local_minibatch(real, n_real, z_d, z_g)
+            orc.aggregate()
+            if r >= warmup:
+                times.append(time.perf_counter() - t0)
+        total = sum(times)
+        return W * len(times) / total, total / len(times)
     orc = OracleMD(args.algo, W, S, B, shape, iid=1)
     g = torch.Generator().manual_seed(1)
     real = torch.tanh(torch.randn(1, W, B, d, generator=g))
@@ -185,17 +211,36 @@ def run_b200(args):
     d = 784 if args.dataset == "mnist" else 2
     C, per, B = args.clients, args.clients_per_server, 100
     S = C // per
-    k = Knobs(num_workers=C, num_servers=S, batch_size=B, epoch=1, cloud_epoch=1, segema=0.0, iid=1, img_shape=shape)
     torch.manual_seed(20211212 + rank)
-    sizes = [3000] * C
-    sim = MDStyleSim(args.algo, k, part_sizes=sizes, device=dev, comm=comm, server_offset=rank * S,
-                     total_data_len=3000 * C * world)
-    # random-init weights of the reference architectures (torch default init), a few distinct modules tiled
-    g_proto = [sim.G.make_module() for _ in range(4)]
-    d_arch = abi.ARCH_D_2D if d == 2 else (abi.ARCH_D_MNIST2 if sim.loss_kind == abi.LOSS_CE else abi.ARCH_D_MNIST1)
-    d_proto = [models.Discriminator(shape, arch=d_arch) for _ in range(8)]
-    sim.G.load_modules([g_proto[s % 4] for s in range(S)])
-    sim.bank.load_modules([d_proto[c % 8] for c in range(C)])
+    fl = args.algo == "flgan"
+    if fl:
+        from cgl_gan_b200.sim import FLStyleSim
+        k = Knobs(num_workers=C, num_servers=1, batch_size=B, img_shape=shape)
+        sim = FLStyleSim(k, device=dev, comm=comm)
+        sim.profile = False
+        g_proto = [sim.G.make_module() for _ in range(4)]
+        d_proto = [models.Discriminator(shape) for _ in range(8)]
+        sim.G.load_modules([g_proto[c % 4] for c in range(C)])
+        sim.bank.load_modules([d_proto[c % 8] for c in range(C)])
+
+        def fl_step(real, n_real):
+            """one local minibatch on every client, then Server.run's average (flgan.py:143-163)"""
+            d_loss, g_loss = sim.local_minibatch(real, n_real)
+            sim.aggregate()
+            return g_loss
+        sim.round = fl_step
+        sim.client_step_ms = lambda: None
+    else:
+        k = Knobs(num_workers=C, num_servers=S, batch_size=B, epoch=1, cloud_epoch=1, segema=0.0, iid=1, img_shape=shape)
+        sizes = [3000] * C
+        sim = MDStyleSim(args.algo, k, part_sizes=sizes, device=dev, comm=comm, server_offset=rank * S,
+                         total_data_len=3000 * C * world)
+        # random-init weights of the reference architectures (torch default init), a few distinct modules tiled
+        g_proto = [sim.G.make_module() for _ in range(4)]
+        d_arch = abi.ARCH_D_2D if d == 2 else (abi.ARCH_D_MNIST2 if sim.loss_kind == abi.LOSS_CE else abi.ARCH_D_MNIST1)
+        d_proto = [models.Discriminator(shape, arch=d_arch) for _ in range(8)]
+        sim.G.load_modules([g_proto[s % 4] for s in range(S)])
+        sim.bank.load_modules([d_proto[c % 8] for c in range(C)])
 
     # synthetic MNIST-shaped batches: a ring of pinned host buffers (e2e) and device-resident copies (value)
     ring = 2
@@ -205,7 +250,7 @@ def run_b200(args):
     n_real_host = torch.full((C,), B, dtype=torch.int32).pin_memory()
     n_real_dev = n_real_host.to(dev)
     stage = [torch.empty(C, B, d, device=dev) for _ in range(2)]
-    loss_host = torch.empty(S, per, dtype=torch.float32).pin_memory()
+    loss_host = (torch.empty(C, dtype=torch.float32) if fl else torch.empty(S, per, dtype=torch.float32)).pin_memory()
 
     def sync_all():
         torch.cuda.synchronize()
