@@ -1,4 +1,4 @@
 set -x
 cd $GRAFT_REPO_ROOT
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_final.log 2>&1; tail -3 gpurun_out/pytest_gpu_final.log
-bash profiles/scripts/g15.sh 8
+bash profiles/scripts/bench_multi_gpu.sh 8
