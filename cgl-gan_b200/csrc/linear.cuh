@@ -8,11 +8,14 @@
 // can pin one for tests and profiling).
 #pragma once
 #include "builders.cuh"
+#include "narrow.cuh"
 #include "tc_persist.cuh"
 
 namespace cgl {
 
 enum { GEMM_AUTO = 0, GEMM_FFMA = 1, GEMM_TC = 2 };
+// narrow layers leave the GEMM kernels in the automatic mode only (GEMM_FFMA / GEMM_TC pin one GEMM kernel for tests)
+static inline bool narrow_wanted(int in, int out);
 int gemm_mode();  // defined in dstep.cu
 
 // db[g][o] = sum_r dy[g][r][o], then either stored or applied as an Adam step on the bias.
@@ -48,6 +51,8 @@ __global__ void __launch_bounds__(128) bias_grad_kernel(int rows, int out, const
   }
 }
 
+static inline bool narrow_wanted(int in, int out) { return gemm_mode() == GEMM_AUTO && narrow_ok(in, out); }
+
 static inline bool tc_wanted(int m_dim, int k_dim, bool operands_ok) {
   const int mode = gemm_mode();
   if (mode == GEMM_FFMA) return false;
@@ -65,6 +70,13 @@ static inline cudaError_t run_linear_fwd(int G, int rows, int in, int out, const
   // algorithmic traffic: W, b, x read once, y written once
   ProfScope prof(tc ? CGL_PROF_FWD_TC : CGL_PROF_FWD_FFMA,
                  4.0 * G * ((double)out * in + out + (double)rows * in + (double)rows * out), 2.0 * G * rows * (double)in * out, st);
+  if (!tc && narrow_wanted(in, out)) {
+    dim3 grid(G, narrow_grid_y(rows * out));
+    narrow_fwd_kernel<<<grid, NARROW_THREADS, (size_t)(out * in + out) * sizeof(float), st>>>(
+        rows, in, out, X, params, ldp, ids, w_off, b_off, act, slope, y, y_gstride);
+    count_launch();
+    return cudaGetLastError();
+  }
   if (tc) {
     TcParams p = {};
     p.M = out; p.N = rows; p.K = in;
@@ -93,6 +105,13 @@ static inline cudaError_t run_linear_bwd_data(int G, int rows, int in, int out, 
   ProfScope prof(tc ? CGL_PROF_BWD_TC : CGL_PROF_BWD_FFMA,
                  4.0 * G * ((double)out * in + (double)rows * out + (saved ? 2.0 : 1.0) * rows * in),
                  2.0 * G * rows * (double)in * out, st);
+  if (!tc && narrow_wanted(in, out)) {
+    dim3 grid(G, narrow_grid_y(rows * in));
+    narrow_bwd_data_kernel<<<grid, NARROW_THREADS, (size_t)out * in * sizeof(float), st>>>(
+        rows, in, out, dy, dy_gstride, params, ldp, ids, w_off, saved, saved_gstride, act, slope, dx, dx_gstride);
+    count_launch();
+    return cudaGetLastError();
+  }
   if (tc) {
     TcParams p = {};
     p.M = in; p.N = rows; p.K = out;
@@ -152,6 +171,17 @@ static inline cudaError_t run_linear_wgrad(int G, int rows, int in, int out, con
   const double nparam = (double)out * in + (b_off >= 0 ? out : 0);
   ProfScope prof(adam ? (tc ? CGL_PROF_WGRAD_ADAM_TC : CGL_PROF_WGRAD_ADAM_FFMA) : (tc ? CGL_PROF_WGRAD_TC : CGL_PROF_WGRAD_FFMA),
                  G * ((adam ? 24.0 : 4.0) * nparam + 4.0 * rows * ((double)in + out)), 2.0 * G * rows * (double)in * out, st);
+  if (!tc && narrow_wanted(in, out)) {
+    if (adam)
+      narrow_wgrad_kernel<true><<<G, NARROW_THREADS, 0, st>>>(rows, in, out, dy, dy_gstride, X, base, ld, ids, w_off, b_off,
+                                                             adam->m, adam->v, adam->step, adam->lr, adam->b1, adam->b2,
+                                                             adam->eps, adam->scal);
+    else
+      narrow_wgrad_kernel<false><<<G, NARROW_THREADS, 0, st>>>(rows, in, out, dy, dy_gstride, X, base, ld, ids, w_off, b_off,
+                                                              nullptr, nullptr, nullptr, 0.f, 0.f, 0.f, 0.f, nullptr);
+    count_launch();
+    return cudaGetLastError();
+  }
   if (tc) {
     TcParams p = {};
     p.M = in; p.N = out; p.K = rows;
