@@ -460,12 +460,19 @@ static int launch_head(const cgl_mlp_desc* a, const cgl_mlp_layout& lay, int G, 
   const bool stream_ok = h.H % 4 == 0 && h.H <= HEAD_MAXJ * HEAD_THREADS && aligned16(h.hin) && aligned16(h.dz) &&
                          h.hin_gstride % 4 == 0 && h.dz_gstride % 4 == 0 && smem_stream <= 200 * 1024;
   ProfScope prof(CGL_PROF_HEAD, 8.0 * G * rows * (double)h.H, 0.0, st);   // last hidden read, its gradient written
+  // the opt-in attribute is raised only when a launch needs more than any launch before it (no runtime call per launch:
+  // a captured round -- MDStyleSim.round_graph -- replays exactly the kernels an eager round launched)
+  static size_t attr_stream = 0, attr_plain = 48 * 1024;
   if (stream_ok) {
-    CGL_CHECK_CUDA(cudaFuncSetAttribute(head_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_stream));
+    if (smem_stream > attr_stream) {
+      CGL_CHECK_CUDA(cudaFuncSetAttribute(head_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_stream));
+      attr_stream = smem_stream;
+    }
     head_stream_kernel<<<G, HEAD_THREADS, smem_stream, st>>>(h);
   } else {
-    if (smem > 48 * 1024) {
+    if (smem > attr_plain) {
       CGL_CHECK_CUDA(cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_plain = smem;
     }
     head_kernel<<<G, HEAD_THREADS, smem, st>>>(h);
   }

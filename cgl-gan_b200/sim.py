@@ -184,6 +184,42 @@ class MDStyleSim:
         self.t += 1
         return loss
 
+    # ---- the same round as a CUDA graph ------------------------------------------------------------
+    def round_graph(self, real, n_real=None, z_d=None, z_g=None):
+        """round() replayed from a CUDA graph: for small topologies (the repo-default 10 workers / 5 servers, the 2DMG
+        networks) a round is ~50 launches of 10-300 us and the host's launch rate, not the GPU, sets the pace.
+        The first call runs an eager round (it also sizes every workspace), the second captures, all later calls copy
+        the inputs into the captured buffers and replay. Fixed control flow only: cloud_epoch in {0, 1}, E == 0, one
+        process; z_d / z_g must be given either always or never (never: torch.randn inside the graph)."""
+        k = self.k
+        assert k.E == 0 and k.cloud_epoch in (0, 1) and self.comm is None and not self.profile, "round_graph: unsupported knobs"
+        st = getattr(self, "_graph_state", None)
+        if st is None:
+            self._graph_state = {"graph": None}
+            return self.round(real, n_real, z_d, z_g)
+        if st["graph"] is None:
+            st["real"] = real.clone()
+            st["n_real"] = None if n_real is None else n_real.clone()
+            st["z_d"] = None if z_d is None else z_d.clone()
+            st["z_g"] = None if z_g is None else z_g.clone()
+            t0 = self.t
+            graph = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            with torch.cuda.graph(graph):
+                st["loss"] = self.round(st["real"], st["n_real"], st["z_d"], st["z_g"])
+            self.t = t0                      # capturing records the kernels, it does not run them
+            st["graph"] = graph
+        else:
+            st["real"].copy_(real)
+            if n_real is not None:
+                st["n_real"].copy_(n_real)
+            if z_d is not None:
+                st["z_d"].copy_(z_d)
+                st["z_g"].copy_(z_g)
+        st["graph"].replay()
+        self.t += 1
+        return st["loss"]
+
     def _server_weights(self, loss):
         """Per-client weight of its G loss in the server objective; also advances Lambda."""
         beta, Lam = self.beta, self.Lambda
@@ -197,7 +233,8 @@ class MDStyleSim:
             F_gamma = (gamma * loss).sum(1)
             self.last_F_max = (F_beta + F_gamma) / 2
             grad = (loss * loss * gamma).sum(1) - (loss * gamma * F_gamma.unsqueeze(1)).sum(1)
-            self.Lambda = Lam + 10 * grad
+            new_lambda = Lam + 10 * grad
+            self.Lambda.copy_(new_lambda)     # in place: a captured round (round_graph) must find its state where it left it
             return (beta + gamma) / 2
         if kind == "cap":                       # capgan.py:247-249
             alpha = F.softmax(Lam.unsqueeze(1) * loss, dim=1)
@@ -211,7 +248,7 @@ class MDStyleSim:
             raise ValueError(kind)
         self.last_F_max = (alpha * loss).sum(1) - 0.001 * Lam
         # opti_L = SGD([Lambda], lr=0.1); dF_max/dLambda = -0.001 (capgan.py:160,250,259)
-        self.Lambda = Lam.add(torch.full_like(Lam, -0.001), alpha=-0.1)
+        self.Lambda.copy_(Lam.add(torch.full_like(Lam, -0.001), alpha=-0.1))
         return alpha
 
     # ---- aggregation ------------------------------------------------------------------------------

@@ -152,3 +152,33 @@ def test_fl_round_matches_oracle(lib, gemm_mode, shape):
         m = sim.G.make_module()
         sim.G.store_module(c, m)
         _compare_generators(m, orc.net_g[c], 4, ("G", c), bulk=1e-4)
+
+
+@pytest.mark.parametrize("shape", [(2,), (1, 28, 28)])
+def test_round_graph_replays_the_eager_round(lib, shape):
+    """MDStyleSim.round_graph (one eager round, one captured, then replays) is bit-identical to round() on the same inputs."""
+    from cgl_gan_b200.sim import Knobs, MDStyleSim
+    torch.manual_seed(5)
+    W, S, B = 8, 4, 100
+    d = 1
+    for s in shape:
+        d *= s
+    k = Knobs(num_workers=W, num_servers=S, batch_size=B, epoch=1, segema=0.25, iid=1, img_shape=shape)
+    sizes = [700 + 31 * i for i in range(W)]
+    a, b = MDStyleSim("cglgan", k, part_sizes=sizes), MDStyleSim("cglgan", k, part_sizes=sizes)
+    g_mods = [a.G.make_module() for _ in range(S)]
+    from cgl_gan_b200 import models
+    d_mods = [models.Discriminator(shape) for _ in range(W)]
+    a.load(g_mods, d_mods)
+    b.load(g_mods, d_mods)
+    for r in range(5):
+        real, n_real, z_d, z_g = _inputs(W, S, B, d, 1, seed=200 + r)
+        real, n_real, z_d, z_g = real[0].cuda(), n_real[0].cuda(), z_d.cuda(), z_g.cuda()
+        la = a.round(real, n_real, z_d, z_g)
+        lb = b.round_graph(real, n_real, z_d, z_g)
+        assert torch.equal(la, lb), r
+    torch.cuda.synchronize()
+    assert a.t == b.t == 5
+    assert torch.equal(a.bank.params, b.bank.params) and torch.equal(a.bank.adam_v, b.bank.adam_v)
+    assert torch.equal(a.G.trunk.params, b.G.trunk.params) and torch.equal(a.G.heads.params, b.G.heads.params)
+    assert torch.equal(a.Lambda, b.Lambda)
