@@ -152,26 +152,32 @@ class StackedGenerator:
         return torch.cat([t, h], dim=1)
 
     # ---- forward ---------------------------------------------------------------------------------
-    def _fwd(self, bank, x, x_idx, B, out_dim):
-        y = torch.empty(bank.rows, B, out_dim, device=self.device)
+    def _fwd(self, bank, x, x_idx, B, out_dim, ids=None):
+        G = bank.rows if ids is None else ids.numel()      # ids: the bank rows that take part (FeGAN's group of the round)
+        y = torch.empty(G, B, out_dim, device=self.device)
         ws = bank.workspace(B)
         lay = bank.lay
-        abi.check(abi.lib.cgl_mlp_forward(C.byref(bank.desc), bank.rows, abi.ptr(bank.params), lay.ld, None,
+        abi.check(abi.lib.cgl_mlp_forward(C.byref(bank.desc), G, abi.ptr(bank.params), lay.ld, abi.ptr(ids),
                                           abi.ptr(bank.stats), lay.ld_stats, 1 if self.training else 0, abi.ptr(x),
                                           B * lay.dims[0], abi.ptr(x_idx), B, abi.ptr(y), abi.ptr(ws), ws.numel(),
                                           _stream()))
         self.launches += bank.n_kernels(False)
         return y
 
-    def forward(self, z):
+    def forward(self, z, ids=None):
         """z [S, B, 100] -> plain: [S, B, d]; multi-head: [S, N, B, d] (head i of server s feeds its
         i-th client, torch.chunk(net_g(z), N) in CGLGAN/2DMG/main.py:231). The activations of the LATEST
         forward are what backward_step differentiates (the reference's Xg pass comes after its no_grad
         Xd pass, CGLGAN/2DMG/main.py:229-234)."""
         S, N = self.S, self.N
+        if ids is not None:
+            assert N == 0, "row subsets are for single-path generators (FL-style clients)"
+            ids = ids.to(device=self.device, dtype=torch.int32).contiguous()
+            S = ids.numel()
         z = z.reshape(S, -1, self.trunk.lay.dims[0]).contiguous().float()
         B = z.shape[1]
-        t_out = self._fwd(self.trunk, z, None, B, self.trunk.lay.dims[-1])
+        t_out = self._fwd(self.trunk, z, None, B, self.trunk.lay.dims[-1], ids)
+        self._last_ids = ids
         if N == 0:
             self._last = (z, t_out, None)
             return t_out
@@ -189,12 +195,13 @@ class StackedGenerator:
         return self.train(False)
 
     # ---- backward + optimiser --------------------------------------------------------------------
-    def _bwd(self, bank, x, x_idx, y, dy, B, want_dx):
+    def _bwd(self, bank, x, x_idx, y, dy, B, want_dx, ids=None):
         lay = bank.lay
-        dx = torch.empty(bank.rows, B, lay.dims[0], device=self.device) if want_dx else None
+        G = bank.rows if ids is None else ids.numel()
+        dx = torch.empty(G, B, lay.dims[0], device=self.device) if want_dx else None
         ws = bank.workspace(B)
-        abi.check(abi.lib.cgl_mlp_backward(C.byref(bank.desc), bank.rows, abi.ptr(bank.params), abi.ptr(bank.adam_m),
-                                           abi.ptr(bank.adam_v), lay.ld, abi.ptr(bank.step), None, C.byref(self.cfg),
+        abi.check(abi.lib.cgl_mlp_backward(C.byref(bank.desc), G, abi.ptr(bank.params), abi.ptr(bank.adam_m),
+                                           abi.ptr(bank.adam_v), lay.ld, abi.ptr(bank.step), abi.ptr(ids), C.byref(self.cfg),
                                            abi.ptr(x), B * lay.dims[0], abi.ptr(x_idx), B, abi.ptr(y), abi.ptr(dy),
                                            abi.ptr(dx), abi.ptr(ws), ws.numel(), _stream()))
         self.launches += bank.n_kernels(True)
@@ -212,7 +219,8 @@ class StackedGenerator:
         B = z.shape[1]
         dy = dy.contiguous().float()
         if N == 0:
-            self._bwd(self.trunk, z, None, t_out, dy.reshape(S, B, -1), B, False)
+            ids = getattr(self, "_last_ids", None)
+            self._bwd(self.trunk, z, None, t_out, dy.reshape(z.shape[0], B, -1), B, False, ids)
         else:
             dh = self._bwd(self.heads, t_out, self.head_src, h_out, dy.reshape(S * N, B, self.d), B, True)
             hid = t_out.shape[2]

@@ -335,18 +335,19 @@ class FLStyleSim:
         self.G.load_modules([g_module] * self.C)
         self.bank.load_modules([d_module] * self.C)
 
-    def local_minibatch(self, real, n_real=None, z_d=None, z_g=None):
-        """One D step + one G step on every client (flgan.py:251-269)."""
-        C, B = self.C, self.B
+    def local_minibatch(self, real, n_real=None, z_d=None, z_g=None, client_ids=None):
+        """One D step + one G step on every client (flgan.py:251-269), or on the clients listed in client_ids
+        (int32 device tensor: FeGAN's group of the round; real / z then hold one entry per listed client)."""
+        C, B = (self.C if client_ids is None else client_ids.numel()), self.B
         if z_d is None:
             z_d = torch.randn(C, B, 100, device=self.device)
         if z_g is None:
             z_g = torch.randn(C, B, 100, device=self.device)
         G = self.G
-        Xd = G(z_d)   # the G grads D_loss.backward() leaves behind are zeroed at flgan.py:264: a plain forward
-        d_loss = self.bank.d_step(real, Xd.reshape(C, B, self.d), n_real=n_real)
-        Xg = G(z_g)
-        g_loss, dxg = self.bank.g_loss_raw(Xg.reshape(C, B, self.d))
+        Xd = G(z_d, ids=client_ids)   # the G grads D_loss.backward() leaves behind are zeroed at flgan.py:264: a plain forward
+        d_loss = self.bank.d_step(real, Xd.reshape(C, B, self.d), n_real=n_real, client_ids=client_ids)
+        Xg = G(z_g, ids=client_ids)
+        g_loss, dxg = self.bank.g_loss_raw(Xg.reshape(C, B, self.d), client_ids=client_ids)
         G.backward_step(dxg)     # g_loss.backward(); opti_g.step()  (flgan.py:266-269)
         return d_loss, g_loss
 
@@ -361,4 +362,43 @@ class FLStyleSim:
                 g = torch.empty(ld, device=self.device)
                 _wsum(self.w, None, buf, ld, g, self.comm)
                 _bcast(None, 0.0, g, buf, ld, rows_n=self.C)
+        self.t += 1
+
+
+class FeGANSim(FLStyleSim):
+    """FeGAN (fegan.py:125-165, 220-303): every round ONE group of clients (partition.init_groups, frac_workers of
+    the population) receives the global G and D -- parameters only: SerializationTool.deserialize_model leaves
+    BatchNorm running statistics and the Adam state with the client -- trains locally like an FL-GAN client, and
+    the server replaces the global vectors by fedavg_aggregate over the group with weights softmax(sk), sk the
+    clients' KL scores (fegan.py:142-146,163-164)."""
+
+    def __init__(self, knobs, sk, groups, device="cuda"):
+        super().__init__(knobs, device=device)
+        self.sk = torch.as_tensor(sk, dtype=torch.float32)
+        self.groups = [list(g) for g in groups]
+        self.p_g = torch.zeros(self.G.trunk.lay.ld, device=self.device)
+        self.p_d = torch.zeros(self.bank.ld, device=self.device)
+
+    def load_global(self, g_module, d_module):
+        """p_g / p_d = serialize_model of the server's fresh networks (fegan.py:133-134)."""
+        from .layout import flatten_params
+        fg, fd = flatten_params(g_module).float(), flatten_params(d_module).float()
+        self.p_g.zero_()
+        self.p_g[:fg.numel()].copy_(fg)
+        self.p_d.zero_()
+        self.p_d[:fd.numel()].copy_(fd)
+
+    def begin_round(self):
+        """-> (group, ids): the round's clients; the global vectors are loaded into their rows."""
+        group = self.groups[self.t % len(self.groups)]
+        ids = torch.tensor(group, dtype=torch.int32, device=self.device)
+        _bcast(ids, 0.0, self.p_d, self.bank.params, self.bank.ld)
+        _bcast(ids, 0.0, self.p_g, self.G.trunk.params, self.G.trunk.lay.ld)
+        return group, ids
+
+    def end_round(self, group, ids):
+        w = torch.exp(self.sk[group])                  # weight = exp(sk); weight /= weight.sum()
+        w = (w / w.sum()).to(self.device)
+        _wsum(w, ids, self.bank.params, self.bank.ld, self.p_d, None)
+        _wsum(w, ids, self.G.trunk.params.detach(), self.G.trunk.lay.ld, self.p_g, None)
         self.t += 1

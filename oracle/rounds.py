@@ -154,3 +154,47 @@ class OracleFL:
         self.p_d = st.fl_aggregate([st.copy_parameters(n) for n in self.net_d], self.C)
         self.p_g = st.fl_aggregate([st.copy_parameters(n) for n in self.net_g], self.C)
         self.load_global()
+
+
+class OracleFeGAN:
+    """FeGAN: Server.run's group loop (fegan.py:125-165) and Worker.run / train (:220-303), clients served serially."""
+
+    def __init__(self, num_workers, batch_size, img_shape, sk, groups, lr=0.0002, b1=0.5, b2=0.999):
+        d = 1
+        for s in img_shape:
+            d *= s
+        two_d = d == 2
+        self.C, self.B = num_workers, batch_size
+        mk_g = (lambda: om.Generator2DMD(img_shape)) if two_d else (lambda: om.GeneratorMNIST(img_shape))
+        mk_d = (lambda: om.Discriminator2D()) if two_d else (lambda: om.DiscriminatorMNIST1(img_shape))
+        self.srv_g, self.srv_d = mk_g(), mk_d()                       # Server.run: fresh net_g / net_d, :127-131
+        self.net_g = [mk_g() for _ in range(self.C)]                  # Worker.run: its own networks, :222-223
+        self.net_d = [mk_d() for _ in range(self.C)]
+        self.opti_g = [st.make_adam(g.parameters(), lr, b1, b2) for g in self.net_g]
+        self.opti_d = [st.make_adam(d_.parameters(), lr, b1, b2) for d_ in self.net_d]
+        self.loss = st.make_loss(st.LOSS_BCE)
+        self.p_g = st.serialize_model(self.srv_g)                     # :133-134
+        self.p_d = st.serialize_model(self.srv_d)
+        self.sk = torch.as_tensor(sk, dtype=torch.float32)
+        self.groups = [list(g) for g in groups]
+        self.t = 0
+
+    def round(self, minibatches):
+        """minibatches: list of (real [N, B, d], n_real [N], z_d [N, B, 100], z_g [N, B, 100]) for the round's group."""
+        group = self.groups[self.t % len(self.groups)]
+        weight = torch.exp(self.sk[group])                            # :142-146
+        weight /= weight.sum()
+        for c in group:                                               # Worker.run, :228-233
+            st.deserialize_model(self.net_g[c], self.p_g)
+            st.deserialize_model(self.net_d[c], self.p_d)
+        out = []
+        for real, n_real, z_d, z_g in minibatches:                    # Worker.train, :282-303
+            dl, gl = torch.zeros(len(group)), torch.zeros(len(group))
+            for j, c in enumerate(group):
+                dl[j], gl[j] = st.fl_local_minibatch(self.net_d[c], self.net_g[c], self.loss, self.opti_g[c], self.opti_d[c],
+                                                     real[j, :int(n_real[j])], z_d[j], z_g[j], self.B)
+            out.append((dl, gl))
+        self.p_g = st.fedavg_aggregate([st.serialize_model(self.net_g[c]) for c in group], weights=weight)   # :163-164
+        self.p_d = st.fedavg_aggregate([st.serialize_model(self.net_d[c]) for c in group], weights=weight)
+        self.t += 1
+        return out

@@ -6,7 +6,7 @@ import pytest
 import torch
 
 from helpers import assert_params_close, bn_fed_biases, max_abs, quantile_err, rel_err, rel_l2
-from oracle.rounds import OracleFL, OracleMD
+from oracle.rounds import OracleFeGAN, OracleFL, OracleMD
 
 pytestmark = pytest.mark.gpu
 
@@ -182,3 +182,49 @@ def test_round_graph_replays_the_eager_round(lib, shape):
     assert torch.equal(a.bank.params, b.bank.params) and torch.equal(a.bank.adam_v, b.bank.adam_v)
     assert torch.equal(a.G.trunk.params, b.G.trunk.params) and torch.equal(a.G.heads.params, b.G.heads.params)
     assert torch.equal(a.Lambda, b.Lambda)
+
+
+@pytest.mark.parametrize("shape", [(2,), (1, 28, 28)])
+def test_fegan_round_matches_oracle(lib, gemm_mode, shape):
+    """FeGAN (BASELINE config[3], frac_workers sampling): per round one group of clients loads the global G / D
+    (parameters only), trains two local minibatches, and the server takes the softmax(sk)-weighted fedavg."""
+    from cgl_gan_b200.sim import FeGANSim, Knobs
+    torch.manual_seed(11)
+    C, B = 6, 100
+    d = 1
+    for s in shape:
+        d *= s
+    sk = [0.3, 0.1, 0.7, 0.2, 0.5, 0.9]
+    groups = [[0, 3], [4, 1, 5], [2, 0], [5, 3, 1]]                       # overlapping groups of 2-3 of the 6 clients
+    orc = OracleFeGAN(C, B, shape, sk, groups)
+    sim = FeGANSim(Knobs(num_workers=C, num_servers=1, batch_size=B, img_shape=shape), sk, groups)
+    sim.G.load_modules(orc.net_g)                                         # every Worker's own fresh networks
+    sim.bank.load_modules(orc.net_d)
+    sim.load_global(orc.srv_g, orc.srv_d)
+    g = torch.Generator().manual_seed(3)
+    for r in range(len(groups)):
+        N = len(groups[r])
+        mbs = []
+        for mb in range(2):
+            real = torch.tanh(torch.randn(N, B, d, generator=g))
+            n_real = torch.full((N,), B, dtype=torch.int32)
+            n_real[0] = 57
+            real[0, 57:] = 0
+            mbs.append((real, n_real, torch.randn(N, B, 100, generator=g), torch.randn(N, B, 100, generator=g)))
+        ref = orc.round(mbs)
+        group, ids = sim.begin_round()
+        assert group == groups[r]
+        for (real, n_real, z_d, z_g), (dl_ref, gl_ref) in zip(mbs, ref):
+            dl, gl = sim.local_minibatch(real.cuda(), n_real.cuda(), z_d.cuda(), z_g.cuda(), client_ids=ids)
+            assert (dl.cpu() - dl_ref).abs().max() < 1e-4 and (gl.cpu() - gl_ref).abs().max() < 1e-4
+        sim.end_round(group, ids)
+    torch.cuda.synchronize()
+    steps = 2 * len(groups)
+    assert_params_close(sim.p_d[:orc.p_d.numel()], orc.p_d, steps=steps, tag="p_d", strict=False, bulk=1e-4)
+    assert_params_close(sim.p_g[:orc.p_g.numel()], orc.p_g, steps=steps, tag="p_g", strict=False, bulk=1e-4)
+    for c in range(C):
+        ref_d = torch.cat([p.detach().reshape(-1) for p in orc.net_d[c].parameters()])
+        assert_params_close(sim.bank.rows()[c], ref_d, steps=steps, tag=("D", c), strict=False, bulk=1e-4)
+        m = sim.G.make_module()
+        sim.G.store_module(c, m)
+        _compare_generators(m, orc.net_g[c], steps, ("G", c), bulk=1e-4)
