@@ -65,6 +65,7 @@ lib.cgl_adam_rows.argtypes = [_i32, _i64, _i64, _p, _p, _p, _p, _p, _f32, _f32, 
 lib.cgl_mix_csr.argtypes = [_i32, _i64, _p, _p, _p, _p, _i64, _p, _i64, _p]
 lib.cgl_wsum.argtypes = [_i32, _i64, _p, _p, _p, _i64, _p, _p]
 lib.cgl_bcast_mix.argtypes = [_i32, _i64, _p, _f32, _p, _p, _i64, _p]
+lib.cgl_wsum_div.argtypes = [_i32, _i64, _f32, _i32, _p, _p, _i64, _p, _p]
 lib.cgl_comm_unique_id.argtypes = [_p]
 lib.cgl_comm_init.argtypes = [_i32, _i32, _p, C.POINTER(_p)]
 lib.cgl_comm_destroy.argtypes = [_p]
@@ -94,7 +95,7 @@ lib.cgl_linear_bwd_data.argtypes = [_i32, _i32, _i32, _i32, _p, _i64, _p, _i64, 
 lib.cgl_linear_wgrad.argtypes = [_i32, _i32, _i32, _i32, _p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _p]
 
 for _name in ("cgl_arch_describe", "cgl_mlp_layout_of", "cgl_d_step", "cgl_g_loss", "cgl_dxg_reduce",
-              "cgl_adam_rows", "cgl_mix_csr", "cgl_wsum", "cgl_bcast_mix", "cgl_comm_unique_id",
+              "cgl_adam_rows", "cgl_mix_csr", "cgl_wsum", "cgl_bcast_mix", "cgl_wsum_div", "cgl_comm_unique_id",
               "cgl_comm_init", "cgl_comm_destroy", "cgl_allreduce_sum", "cgl_mix_allreduce",
               "cgl_linear_fwd", "cgl_linear_bwd_data", "cgl_linear_wgrad", "cgl_set_gemm_mode", "cgl_mlp_forward", "cgl_mlp_backward", "cgl_profile_enable",
               "cgl_profile_summary", "cgl_debug_set_timeline", "cgl_linear_wgrad_adam", "cgl_gather_rows", "cgl_hist2d",

@@ -46,6 +46,16 @@ struct ProfScope {
     }                               \
   } while (0)
 
+// cudaFuncSetAttribute is per device: "already done" flags are bit masks over the device ordinal
+static inline bool first_use_on_device(unsigned long long& mask) {
+  int d = 0;
+  cudaGetDevice(&d);
+  const unsigned long long b = 1ull << (d & 63);
+  if (mask & b) return false;
+  mask |= b;
+  return true;
+}
+
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // ---- Adam (torch.optim.Adam, single-tensor path; reference a7: CGLGAN/2DMG/main.py:192,337) --

@@ -462,7 +462,13 @@ static int launch_head(const cgl_mlp_desc* a, const cgl_mlp_layout& lay, int G, 
   ProfScope prof(CGL_PROF_HEAD, 8.0 * G * rows * (double)h.H, 0.0, st);   // last hidden read, its gradient written
   // the opt-in attribute is raised only when a launch needs more than any launch before it (no runtime call per launch:
   // a captured round -- MDStyleSim.round_graph -- replays exactly the kernels an eager round launched)
-  static size_t attr_stream = 0, attr_plain = 48 * 1024;
+  // (the attribute is per device: the high-water marks are kept per device ordinal)
+  static size_t attr_stream_dev[64] = {}, attr_plain_dev[64] = {};
+  int dev = 0;
+  CGL_CHECK_CUDA(cudaGetDevice(&dev));
+  size_t& attr_stream = attr_stream_dev[dev & 63];
+  size_t& attr_plain = attr_plain_dev[dev & 63];
+  if (attr_plain == 0) attr_plain = 48 * 1024;
   if (stream_ok) {
     if (smem_stream > attr_stream) {
       CGL_CHECK_CUDA(cudaFuncSetAttribute(head_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_stream));

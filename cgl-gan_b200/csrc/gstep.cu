@@ -394,11 +394,9 @@ extern "C" int cgl_mlp_forward(const cgl_mlp_desc* arch, int G, const float* par
       dim3 grid((out + 127) / 128, G);
       ProfScope prof(CGL_PROF_BN_FWD, 8.0 * G * rows * (double)out, 0.0, st);   // u read, h written
       if (bn_smem_ok(rows, out, b.u, b.u_gstride, nullptr, 0, 1)) {
-        static bool attr = false;
-        if (!attr) {
+        static unsigned long long attr = 0;
+        if (first_use_on_device(attr))
           CGL_CHECK_CUDA(cudaFuncSetAttribute(bn_fwd_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-          attr = true;
-        }
         bn_fwd_smem_kernel<<<grid, 128, (size_t)rows * 512, st>>>(b);
       } else {
         bn_fwd_kernel<<<grid, 128, 0, st>>>(b);
@@ -461,11 +459,9 @@ extern "C" int cgl_mlp_backward(const cgl_mlp_desc* arch, int G, float* params, 
       dim3 grid((out + 127) / 128, G);
       ProfScope prof(CGL_PROF_BN_BWD, 12.0 * G * rows * (double)out, 0.0, st);  // dz, u read, du written
       if (bn_smem_ok(rows, out, b.dz, b.dz_gstride, b.u, b.u_gstride, 2)) {
-        static bool attr = false;
-        if (!attr) {
+        static unsigned long long attr = 0;
+        if (first_use_on_device(attr))
           CGL_CHECK_CUDA(cudaFuncSetAttribute(bn_bwd_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-          attr = true;
-        }
         bn_bwd_smem_kernel<<<grid, 128, (size_t)rows * 1024, st>>>(b);
       } else {
         bn_bwd_kernel<<<grid, 128, 0, st>>>(b);

@@ -26,7 +26,11 @@ __device__ __forceinline__ void axpy4(float4& acc, float w, const float4& x) {
 }
 
 // dst[r,:] = sum_j vals[j] * src[col[j],:]; the first term initialises (p[key] = paras*A).
-template <bool VEC>
+// MEAN: dst[r,:] = (sum_j src[col[j],:]) / count -- receive_parameter's `p += d ... p /= len` (CGLGAN/2DMG/main.py:171-179).
+__device__ __forceinline__ float4 mul4(const float4& x, float w) {
+  return make_float4(__fmul_rn(x.x, w), __fmul_rn(x.y, w), __fmul_rn(x.z, w), __fmul_rn(x.w, w));
+}
+template <bool VEC, bool MEAN>
 __global__ void __launch_bounds__(MIX_THREADS) mix_csr_kernel(long long n, const int* __restrict__ row_ptr,
                                                              const int* __restrict__ col,
                                                              const float* __restrict__ vals,
@@ -34,6 +38,7 @@ __global__ void __launch_bounds__(MIX_THREADS) mix_csr_kernel(long long n, const
                                                              float* __restrict__ dst, long long ld_dst) {
   const int r = blockIdx.y;
   const int j0 = row_ptr[r], j1 = row_ptr[r + 1];
+  const float cnt = (float)(j1 - j0);
   if (VEC) {
     const long long n4 = n >> 2;
     for (long long i = (long long)blockIdx.x * MIX_THREADS + threadIdx.x; i < n4;
@@ -42,8 +47,7 @@ __global__ void __launch_bounds__(MIX_THREADS) mix_csr_kernel(long long n, const
       int j = j0;
       if (j < j1) {
         float4 x = ld_stream(reinterpret_cast<const float4*>(src + (long long)col[j] * ld_src) + i);
-        float w = vals[j];
-        acc = make_float4(__fmul_rn(x.x, w), __fmul_rn(x.y, w), __fmul_rn(x.z, w), __fmul_rn(x.w, w));
+        acc = MEAN ? x : mul4(x, vals[j]);
         ++j;
       }
       for (; j + 3 < j1; j += 4) {
@@ -51,13 +55,15 @@ __global__ void __launch_bounds__(MIX_THREADS) mix_csr_kernel(long long n, const
         float4 x1 = ld_stream(reinterpret_cast<const float4*>(src + (long long)col[j + 1] * ld_src) + i);
         float4 x2 = ld_stream(reinterpret_cast<const float4*>(src + (long long)col[j + 2] * ld_src) + i);
         float4 x3 = ld_stream(reinterpret_cast<const float4*>(src + (long long)col[j + 3] * ld_src) + i);
-        axpy4(acc, vals[j], x0); axpy4(acc, vals[j + 1], x1);
-        axpy4(acc, vals[j + 2], x2); axpy4(acc, vals[j + 3], x3);
+        axpy4(acc, MEAN ? 1.f : vals[j], x0); axpy4(acc, MEAN ? 1.f : vals[j + 1], x1);     // x * 1 is exact
+        axpy4(acc, MEAN ? 1.f : vals[j + 2], x2); axpy4(acc, MEAN ? 1.f : vals[j + 3], x3);
       }
       for (; j < j1; ++j) {
         float4 x = ld_stream(reinterpret_cast<const float4*>(src + (long long)col[j] * ld_src) + i);
-        axpy4(acc, vals[j], x);
+        axpy4(acc, MEAN ? 1.f : vals[j], x);
       }
+      if (MEAN && j1 > j0)
+        acc = make_float4(__fdiv_rn(acc.x, cnt), __fdiv_rn(acc.y, cnt), __fdiv_rn(acc.z, cnt), __fdiv_rn(acc.w, cnt));
       reinterpret_cast<float4*>(dst + (long long)r * ld_dst)[i] = acc;
     }
   } else {
@@ -65,57 +71,86 @@ __global__ void __launch_bounds__(MIX_THREADS) mix_csr_kernel(long long n, const
          i += (long long)gridDim.x * MIX_THREADS) {
       float acc = 0.f;
       for (int j = j0; j < j1; ++j) {
-        float t = __fmul_rn(src[(long long)col[j] * ld_src + i], vals[j]);
+        const float x = src[(long long)col[j] * ld_src + i];
+        const float t = MEAN ? x : __fmul_rn(x, vals[j]);
         acc = (j == j0) ? t : __fadd_rn(acc, t);
       }
+      if (MEAN && j1 > j0) acc = __fdiv_rn(acc, cnt);
       dst[(long long)r * ld_dst + i] = acc;
     }
   }
 }
 
-// out[:] = sum_c w[c] * src[rows ? rows[c] : c, :], c in ascending order. Eight rows in flight per
-// thread; the float4 column index is the only parallel axis so the result is order-exact.
-template <bool VEC>
-__global__ void __launch_bounds__(MIX_THREADS) wsum_kernel(int C, long long n, const float* __restrict__ w,
+// out[:] = sum_c term(c), c in ascending order, term(c) = x_c * w[c] (MODE 0: Cloud.run, fedavg_aggregate),
+// x_c / div (MODE 1: `p[key] += paras[key] / len(client_list)`, FLGAN/MNIST/flgan.py:151-158) or x_c with the sum divided
+// by div at the end (MODE 2: receive_parameter, CGLGAN/2DMG/main.py:171-179). Every product / quotient and every sum is
+// rounded separately, in the order the reference's dict loop applies them, so the result is order-exact. The sum over c
+// is a serial fp32 chain per element: the column index is the only parallel axis, and the vector width VW (floats per
+// thread) is chosen by the host so that a short row (a generator trunk: 179 k floats) still spreads over > 100 k threads
+// with U independent loads in flight each.
+template <int VW> struct VecT;
+template <> struct VecT<4> { typedef float4 type; };
+template <> struct VecT<2> { typedef float2 type; };
+template <> struct VecT<1> { typedef float type; };
+template <int VW>
+__device__ __forceinline__ void ld_vec(const float* p, float (&v)[VW]) {
+  if (VW == 4) {
+    const float4 t = ld_stream(reinterpret_cast<const float4*>(p));
+    v[0] = t.x; v[1] = t.y; v[2 % VW] = t.z; v[3 % VW] = t.w;
+  } else if (VW == 2) {
+    float2 t;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(t.x), "=f"(t.y) : "l"(p));
+    v[0] = t.x; v[1 % VW] = t.y;
+  } else {
+    float t;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(t) : "l"(p));
+    v[0] = t;
+  }
+}
+template <int MODE>
+__device__ __forceinline__ float wsum_term(float x, float w, float div) {
+  return MODE == 0 ? __fmul_rn(x, w) : (MODE == 1 ? __fdiv_rn(x, div) : x);
+}
+template <int VW, int MODE>
+__global__ void __launch_bounds__(MIX_THREADS) wsum_kernel(int C, long long n, const float* __restrict__ w, float div,
                                                           const int* __restrict__ rows,
                                                           const float* __restrict__ src, long long ld_src,
                                                           float* __restrict__ out) {
-  if (VEC) {
-    const long long n4 = n >> 2;
-    for (long long i = (long long)blockIdx.x * MIX_THREADS + threadIdx.x; i < n4;
-         i += (long long)gridDim.x * MIX_THREADS) {
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      int c = 0;
-      if (C > 0) {
-        float4 x = ld_stream(reinterpret_cast<const float4*>(src + (long long)(rows ? rows[0] : 0) * ld_src) + i);
-        float ww = w[0];
-        acc = make_float4(__fmul_rn(x.x, ww), __fmul_rn(x.y, ww), __fmul_rn(x.z, ww), __fmul_rn(x.w, ww));
-        c = 1;
-      }
-      for (; c + 7 < C; c += 8) {
-        float4 x[8];
+  constexpr int U = (VW == 4) ? 8 : 16;
+  const long long nv = n / VW;
+  for (long long i = (long long)blockIdx.x * MIX_THREADS + threadIdx.x; i < nv; i += (long long)gridDim.x * MIX_THREADS) {
+    float acc[VW];
 #pragma unroll
-        for (int u = 0; u < 8; ++u)
-          x[u] = ld_stream(reinterpret_cast<const float4*>(src + (long long)(rows ? rows[c + u] : c + u) * ld_src) + i);
+    for (int e = 0; e < VW; ++e) acc[e] = 0.f;
+    int c = 0;
+    if (C > 0) {
+      float x[VW];
+      ld_vec<VW>(src + (long long)(rows ? rows[0] : 0) * ld_src + i * VW, x);
+      const float ww = MODE == 0 ? w[0] : 0.f;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) axpy4(acc, w[c + u], x[u]);
-      }
-      for (; c < C; ++c) {
-        float4 x = ld_stream(reinterpret_cast<const float4*>(src + (long long)(rows ? rows[c] : c) * ld_src) + i);
-        axpy4(acc, w[c], x);
-      }
-      reinterpret_cast<float4*>(out)[i] = acc;
+      for (int e = 0; e < VW; ++e) acc[e] = wsum_term<MODE>(x[e], ww, div);   // the first term initialises (p[key] = ...)
+      c = 1;
     }
-  } else {
-    for (long long i = (long long)blockIdx.x * MIX_THREADS + threadIdx.x; i < n;
-         i += (long long)gridDim.x * MIX_THREADS) {
-      float acc = 0.f;
-      for (int c = 0; c < C; ++c) {
-        float t = __fmul_rn(src[(long long)(rows ? rows[c] : c) * ld_src + i], w[c]);
-        acc = (c == 0) ? t : __fadd_rn(acc, t);
+    for (; c + U - 1 < C; c += U) {
+      float x[U][VW];
+#pragma unroll
+      for (int u = 0; u < U; ++u) ld_vec<VW>(src + (long long)(rows ? rows[c + u] : c + u) * ld_src + i * VW, x[u]);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const float ww = MODE == 0 ? w[c + u] : 0.f;
+#pragma unroll
+        for (int e = 0; e < VW; ++e) acc[e] = __fadd_rn(acc[e], wsum_term<MODE>(x[u][e], ww, div));
       }
-      out[i] = acc;
     }
+    for (; c < C; ++c) {
+      float x[VW];
+      ld_vec<VW>(src + (long long)(rows ? rows[c] : c) * ld_src + i * VW, x);
+      const float ww = MODE == 0 ? w[c] : 0.f;
+#pragma unroll
+      for (int e = 0; e < VW; ++e) acc[e] = __fadd_rn(acc[e], wsum_term<MODE>(x[e], ww, div));
+    }
+#pragma unroll
+    for (int e = 0; e < VW; ++e) out[i * VW + e] = (MODE == 2) ? __fdiv_rn(acc[e], div) : acc[e];
   }
 }
 
@@ -249,15 +284,37 @@ extern "C" int cgl_mix_csr(int R, int64_t n, const int32_t* row_ptr, const int32
                            const float* src, int64_t ld_src, float* dst, int64_t ld_dst, cgl_stream_t stream) {
   if (R == 0 || n == 0) return CGL_OK;
   CGL_REQUIRE(R > 0 && R <= 65535 && n > 0, "bad shape R=%d n=%lld", R, (long long)n);
-  CGL_REQUIRE(row_ptr && col && vals && src && dst, "NULL tensor pointer");
+  CGL_REQUIRE(row_ptr && col && src && dst, "NULL tensor pointer");   // vals == NULL: row means
   CGL_REQUIRE(src != dst, "cgl_mix_csr cannot run in place");
   cudaStream_t st = (cudaStream_t)stream;
   bool vec = aligned16(src) && aligned16(dst) && n % 4 == 0 && ld_src % 4 == 0 && ld_dst % 4 == 0;
   dim3 grid(grid_x(vec ? n / 4 : n, R), R);
   // the column count lives on the device: at least one source row is read per written row
   ProfScope prof(CGL_PROF_MIX, 8.0 * R * (double)n, 0.0, st);
-  if (vec) mix_csr_kernel<true><<<grid, MIX_THREADS, 0, st>>>(n, row_ptr, col, vals, src, ld_src, dst, ld_dst);
-  else mix_csr_kernel<false><<<grid, MIX_THREADS, 0, st>>>(n, row_ptr, col, vals, src, ld_src, dst, ld_dst);
+  if (vals) {
+    if (vec) mix_csr_kernel<true, false><<<grid, MIX_THREADS, 0, st>>>(n, row_ptr, col, vals, src, ld_src, dst, ld_dst);
+    else mix_csr_kernel<false, false><<<grid, MIX_THREADS, 0, st>>>(n, row_ptr, col, vals, src, ld_src, dst, ld_dst);
+  } else {
+    if (vec) mix_csr_kernel<true, true><<<grid, MIX_THREADS, 0, st>>>(n, row_ptr, col, vals, src, ld_src, dst, ld_dst);
+    else mix_csr_kernel<false, true><<<grid, MIX_THREADS, 0, st>>>(n, row_ptr, col, vals, src, ld_src, dst, ld_dst);
+  }
+  CGL_CHECK_LAUNCH();
+  return CGL_OK;
+}
+
+template <int MODE>
+static int launch_wsum(int C, int64_t n, const float* w, float div, const int32_t* rows, const float* src, int64_t ld_src,
+                       float* out, cudaStream_t st) {
+  // widest vector the pointers allow, narrowed until the row spreads over >= ~100 k threads (or VW reaches 1)
+  int vw = (aligned16(src) && aligned16(out) && n % 4 == 0 && ld_src % 4 == 0) ? 4
+           : ((((uintptr_t)src | (uintptr_t)out) & 7u) == 0 && n % 2 == 0 && ld_src % 2 == 0) ? 2 : 1;
+  while (vw > 1 && n / vw < 100000) vw >>= 1;
+  const long long items = n / vw;
+  const int gx = (int)((items + MIX_THREADS - 1) / MIX_THREADS);
+  ProfScope prof(CGL_PROF_MIX, 4.0 * ((double)C + 1.0) * (double)n, 2.0 * C * (double)n, st);   // 4 P (C_in + R_out)
+  if (vw == 4) wsum_kernel<4, MODE><<<gx, MIX_THREADS, 0, st>>>(C, n, w, div, rows, src, ld_src, out);
+  else if (vw == 2) wsum_kernel<2, MODE><<<gx, MIX_THREADS, 0, st>>>(C, n, w, div, rows, src, ld_src, out);
+  else wsum_kernel<1, MODE><<<gx, MIX_THREADS, 0, st>>>(C, n, w, div, rows, src, ld_src, out);
   CGL_CHECK_LAUNCH();
   return CGL_OK;
 }
@@ -267,15 +324,17 @@ extern "C" int cgl_wsum(int C, int64_t n, const float* w, const int32_t* rows, c
   if (n == 0) return CGL_OK;
   CGL_REQUIRE(C >= 0 && n > 0, "bad shape C=%d n=%lld", C, (long long)n);
   CGL_REQUIRE((C == 0 || (w && src)) && out, "NULL tensor pointer");
-  cudaStream_t st = (cudaStream_t)stream;
-  bool vec = aligned16(src) && aligned16(out) && n % 4 == 0 && ld_src % 4 == 0;
-  long long items = vec ? n / 4 : n;
-  int gx = (int)((items + MIX_THREADS - 1) / MIX_THREADS);
-  ProfScope prof(CGL_PROF_MIX, 4.0 * ((double)C + 1.0) * (double)n, 2.0 * C * (double)n, st);   // 4 P (C_in + R_out)
-  if (vec) wsum_kernel<true><<<gx, MIX_THREADS, 0, st>>>(C, n, w, rows, src, ld_src, out);
-  else wsum_kernel<false><<<gx, MIX_THREADS, 0, st>>>(C, n, w, rows, src, ld_src, out);
-  CGL_CHECK_LAUNCH();
-  return CGL_OK;
+  return launch_wsum<0>(C, n, w, 1.f, rows, src, ld_src, out, (cudaStream_t)stream);
+}
+
+extern "C" int cgl_wsum_div(int C, int64_t n, float divisor, int sum_first, const int32_t* rows, const float* src,
+                            int64_t ld_src, float* out, cgl_stream_t stream) {
+  if (n == 0) return CGL_OK;
+  CGL_REQUIRE(C >= 0 && n > 0, "bad shape C=%d n=%lld", C, (long long)n);
+  CGL_REQUIRE((C == 0 || src) && out, "NULL tensor pointer");
+  CGL_REQUIRE(divisor != 0.f, "divisor is zero");
+  if (sum_first) return launch_wsum<2>(C, n, nullptr, divisor, rows, src, ld_src, out, (cudaStream_t)stream);
+  return launch_wsum<1>(C, n, nullptr, divisor, rows, src, ld_src, out, (cudaStream_t)stream);
 }
 
 extern "C" int cgl_bcast_mix(int R, int64_t n, const int32_t* rows, float sigma, const float* g, float* dst,

@@ -712,12 +712,11 @@ static inline int tc_pow2_cols(int cols) {
 
 template <bool A_KMAJOR, bool B_KMAJOR, int EPI, int NB, int OCC, int LW = 8, int BKT = 32>
 static inline cudaError_t launch_tc_gemm_nb(const TcParams& p, int G, cudaStream_t stream) {
-  static bool attr_set = false;  // per template instantiation
-  if (!attr_set) {
+  static unsigned long long attr_set = 0;  // per template instantiation, one bit per device
+  if (first_use_on_device(attr_set)) {
     cudaError_t e = cudaFuncSetAttribute(tc_grouped_gemm_kernel<A_KMAJOR, B_KMAJOR, EPI, NB, OCC, LW, BKT>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BUDGET);
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   const size_t smem = (size_t)p.n_stages * (tc_stage_bytes(p.bn) * BKT / TC_BK) + 1024;
   dim3 grid((p.N + p.bn - 1) / p.bn, (p.M + TC_BM - 1) / TC_BM, G);

@@ -370,21 +370,19 @@ static inline bool launch_tc_persistent(TcParams p, int G, cudaStream_t stream, 
   const int sms = tc_num_sms();
   const int grid = (int)(tiles < sms ? tiles : sms);
   if (p.bn <= 112) {
-    static bool attr7 = false;
-    if (!attr7) {
+    static unsigned long long attr7 = 0;
+    if (first_use_on_device(attr7)) {
       *err = cudaFuncSetAttribute(tc_persistent_gemm_kernel<A_KMAJOR, B_KMAJOR, EPI, 7>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BUDGET);
       if (*err != cudaSuccess) return true;
-      attr7 = true;
     }
     tc_persistent_gemm_kernel<A_KMAJOR, B_KMAJOR, EPI, 7><<<grid, TCP_THREADS, smem, stream>>>(p, G);
   } else {
-    static bool attr8 = false;
-    if (!attr8) {
+    static unsigned long long attr8 = 0;
+    if (first_use_on_device(attr8)) {
       *err = cudaFuncSetAttribute(tc_persistent_gemm_kernel<A_KMAJOR, B_KMAJOR, EPI, 8>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BUDGET);
       if (*err != cudaSuccess) return true;
-      attr8 = true;
     }
     tc_persistent_gemm_kernel<A_KMAJOR, B_KMAJOR, EPI, 8><<<grid, TCP_THREADS, smem, stream>>>(p, G);
   }

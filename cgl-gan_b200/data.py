@@ -19,6 +19,9 @@ from . import abi
 from .engine import _stream
 
 
+STAGING_SLOTS = 4
+
+
 class ResidentPartitions:
     def __init__(self, data, partitions, batch_size, device="cuda", shuffle=True):
         """data: [n, ...] float tensor (moved to the device once); partitions: one sequence of row ids per client."""
@@ -32,15 +35,23 @@ class ResidentPartitions:
         # Worker.__init__: one DataLoader per client, created in client order (each iter() draws from the global RNG)
         self.loaders = [DataLoader(dataset=p, batch_size=self.B, shuffle=shuffle) for p in self.parts]
         self.iters = [iter(dl) for dl in self.loaders]
-        self._idx_host = torch.empty(self.C, self.B, dtype=torch.int64).pin_memory()
-        self._n_host = torch.empty(self.C, dtype=torch.int32).pin_memory()
-        self._idx_dev = torch.empty(self.C, self.B, dtype=torch.int64, device=self.device)
-        self._n_dev = torch.empty(self.C, dtype=torch.int32, device=self.device)
+        # A ring of pinned staging slots: the host runs ahead of the stream (a round enqueues dozens of kernels), so a
+        # slot is rewritten only after the event recorded behind its previous host -> device copy has completed.
+        self._slots = [dict(idx=torch.empty(self.C, self.B, dtype=torch.int64).pin_memory(),
+                            n=torch.empty(self.C, dtype=torch.int32).pin_memory(), ev=None) for _ in range(STAGING_SLOTS)]
+        self._slot = 0
 
-    def next_indices(self):
+    def next_indices(self, slot=None):
         """One `next(self.data)` per client, in client order (Worker.train, main.py:350-355). Returns the pinned
-        [C, B] row ids (-1 = padding of a short last batch) and the valid counts [C]."""
-        idx, n = self._idx_host, self._n_host
+        [C, B] row ids (-1 = padding of a short last batch) and the valid counts [C] of a staging slot that no
+        copy in flight still reads."""
+        if slot is None:
+            slot = self._slots[self._slot]
+            self._slot = (self._slot + 1) % len(self._slots)
+        if slot["ev"] is not None:
+            slot["ev"].synchronize()
+            slot["ev"] = None
+        idx, n = slot["idx"], slot["n"]
         idx.fill_(-1)
         for c in range(self.C):
             try:
@@ -56,14 +67,18 @@ class ResidentPartitions:
 
     def next_batches(self, out=None):
         """-> (real [C, B, d] on the device, n_real [C] int32 on the device) for MDStyleSim.round / FLStyleSim."""
-        idx, n = self.next_indices()
-        self._idx_dev.copy_(idx, non_blocking=True)
-        self._n_dev.copy_(n, non_blocking=True)
+        slot = self._slots[self._slot]
+        self._slot = (self._slot + 1) % len(self._slots)
+        idx, n = self.next_indices(slot)
+        idx_dev = idx.to(self.device, non_blocking=True)      # per-round device tensors: nothing aliases across rounds
+        n_dev = n.to(self.device, non_blocking=True)
+        slot["ev"] = torch.cuda.Event()
+        slot["ev"].record()
         if out is None:
             out = torch.empty(self.C, self.B, self.d, device=self.device)
-        abi.check(abi.lib.cgl_gather_rows(self.C * self.B, self.d, abi.ptr(self.data), self.n, abi.ptr(self._idx_dev),
+        abi.check(abi.lib.cgl_gather_rows(self.C * self.B, self.d, abi.ptr(self.data), self.n, abi.ptr(idx_dev),
                                           abi.ptr(out), _stream()))
-        return out, self._n_dev
+        return out, n_dev
 
     @property
     def h2d_bytes_per_round(self):

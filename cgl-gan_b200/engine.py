@@ -123,11 +123,12 @@ class ClientBank:
         return self._scratch
 
     def mix(self, matrix):
-        """params <- M @ params for a dense [C,C] (or CSR triple) mixing matrix: FedAvg rows, swap
-        permutations, neighbour / group means (a8, a10). Out of place, then the buffers swap roles."""
+        """params <- M @ params for a dense [C,C] (or CSR triple (row_ptr, col, vals)) mixing matrix: FedAvg rows, swap
+        permutations, neighbour / group means (a8, a10); vals None = the mean of the listed rows, summed in column order
+        and divided once (receive_parameter, CGLGAN/2DMG/main.py:171-179). Out of place, then the buffers swap roles."""
         row_ptr, col, vals = dense_to_csr(matrix) if torch.is_tensor(matrix) else matrix
         row_ptr, col = _i32(row_ptr, self.device), _i32(col, self.device)
-        vals = vals.to(self.device, torch.float32).contiguous()
+        vals = None if vals is None else vals.to(self.device, torch.float32).contiguous()   # None: row means (cgl_mix_csr)
         R = row_ptr.numel() - 1
         assert R == self.C
         dst = self._other()

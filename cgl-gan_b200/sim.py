@@ -40,11 +40,12 @@ ALGOS = {
 @dataclass
 class Knobs:
     """The reference's global knobs (CGLGAN/2DMG/main.py:30-58, mixed-gan.py:41-59)."""
+    num_communication: int = 20000   # the round counter t counts DOWN from here (while t > 0: ...; t -= 1)
     num_workers: int = 10
     num_servers: int = 5
     batch_size: int = 100
     epoch: int = 1            # local D steps per round
-    cloud_epoch: int = 1      # rounds between cloud aggregations (0: never)
+    cloud_epoch: int = 1      # rounds between cloud aggregations (0: never); root capgan.py: EPOCHS over the server's data
     segema: float = 0.0       # 1: fully independent servers, 0: fully shared trunk
     E: int = 0                # rounds between neighbour-D shares (0: off, as shipped: commented out)
     frac_workers: float = 1.0
@@ -140,9 +141,9 @@ class MDStyleSim:
             real = real.unsqueeze(0)
         if n_real is not None and n_real.dim() == 1:
             n_real = n_real.unsqueeze(0)
-        if k.cloud_epoch and self.t % k.cloud_epoch == 0:
+        if self._cloud_due():
             self.cloud_aggregate()
-        if k.E and self.t % k.E == 0 and self.t > 0:
+        if self._share_due():
             self.share_discriminators()
         if z_d is None:
             z_d = torch.randn(S, B, 100, device=self.device)
@@ -197,7 +198,14 @@ class MDStyleSim:
         if st is None:
             self._graph_state = {"graph": None}
             return self.round(real, n_real, z_d, z_g)
+        if st["graph"] is not None:
+            given = (n_real is not None, z_d is not None, z_g is not None)
+            if given != st["given"]:
+                raise ValueError(f"round_graph was captured with (n_real, z_d, z_g) given = {st['given']}, now {given}: "
+                                 "a captured round cannot change which inputs it reads")
         if st["graph"] is None:
+            st["given"] = (n_real is not None, z_d is not None, z_g is not None)
+            assert st["given"][1] == st["given"][2], "z_d and z_g must be given together"
             st["real"] = real.clone()
             st["n_real"] = None if n_real is None else n_real.clone()
             st["z_d"] = None if z_d is None else z_d.clone()
@@ -219,6 +227,44 @@ class MDStyleSim:
         st["graph"].replay()
         self.t += 1
         return st["loss"]
+
+    def _cloud_due(self):
+        """The servers' `if t % ... == 0` before Server.train, with the reference's counter t = num_communication - rounds done:
+        CGLGAN/2DMG/main.py:201, mixed-gan.py:193, CAPGAN/MNIST/capgan.py:169: every cloud_epoch rounds;
+        capgan.py:169: `t % (self.data_len * cloud_epoch / batch_size) == 0` -- there cloud_epoch counts EPOCHS over the
+        server's data and the period is a float32 tensor (int % tensor = torch.remainder). The exchange is a rendezvous of
+        all servers with the Cloud (capgan.py:108-117), so servers that disagree would deadlock the reference: refused."""
+        k = self.k
+        if not k.cloud_epoch:
+            return False
+        t_ref = k.num_communication - self.t
+        if self.algo != "capgan":
+            return t_ref % k.cloud_epoch == 0
+        period = self.data_len * k.cloud_epoch / k.batch_size          # float32 [S], as in the reference
+        due = torch.remainder(torch.tensor(float(t_ref)), period) == 0
+        if self.comm is not None:                                      # every rank must take the same decision
+            import torch.distributed as dist
+            flags = torch.tensor([float(due.all()), float(due.any())], device=self.device)
+            dist.all_reduce(flags[0:1], op=dist.ReduceOp.MIN)
+            dist.all_reduce(flags[1:2], op=dist.ReduceOp.MAX)
+            all_due, any_due = bool(flags[0].item()), bool(flags[1].item())
+        else:
+            all_due, any_due = bool(due.all()), bool(due.any())
+        if any_due and not all_due:
+            raise ValueError("capgan: the servers' cloud periods data_len*cloud_epoch/batch_size differ "
+                             f"({period.tolist()}); the reference's Cloud rendezvous (capgan.py:108-117) would deadlock")
+        return all_due
+
+    def _share_due(self):
+        """Neighbour-D share every E rounds. ACGAN counts the rounds done, `(num_communication - t) % E == 0`
+        (ACGAN/MNIST/acgan.py:240: round 0 shares too); MD-GAN tests the down-counter itself, `t % E == 0`
+        (MDGAN/MNIST/mdgan.py:158,258); the scripts without a call site follow MD-GAN."""
+        k = self.k
+        if not k.E:
+            return False
+        if self.algo == "acgan":
+            return self.t % k.E == 0
+        return (k.num_communication - self.t) % k.E == 0
 
     def _server_weights(self, loss):
         """Per-client weight of its G loss in the server objective; also advances Lambda."""
@@ -278,18 +324,23 @@ class MDStyleSim:
         "group_mean": every client of a server ends with the mean D of that server's clients
         (ACGAN/MNIST/acgan.py:240-263 fixed point == CGLGAN/2DMG/main.py:171-179);
         "swap": the server shuffles its clients' Ds (MDGAN/MNIST/mdgan.py:158-164,258-262)."""
-        C, N = self.C, self.N
-        M = torch.zeros(C, C)
+        row_ptr, col = [0], []
         for s, cl in enumerate(self.client_list):
             if self.k.d_share == "swap":
                 order = list(range(len(cl)))
-                self.swap_rd[s].shuffle(order)
-                for j, c in enumerate(cl):
-                    M[c, cl[order[j]]] = 1.0
+                self.swap_rd[s].shuffle(order)          # the shuffle of a list depends on its length only
+                for j, c in enumerate(cl):              # clients are numbered server by server: row c == position in col
+                    col.append(cl[order[j]])
+                    row_ptr.append(len(col))
             else:
                 for c in cl:
-                    M[c, cl] = 1.0 / len(cl)
-        self.bank.mix(M)
+                    col += cl                           # `p += d` over the group in client order, then `p /= len`
+                    row_ptr.append(len(col))
+        row_ptr, col = torch.tensor(row_ptr, dtype=torch.int32), torch.tensor(col, dtype=torch.int32)
+        if self.k.d_share == "swap":
+            self.bank.mix((row_ptr, col, torch.ones(col.numel())))      # a permutation: exact copies
+        else:
+            self.bank.mix((row_ptr, col, None))                         # row means (sum, then one division)
 
 
 def _wsum(w, rows, buf, ld, out, comm):
@@ -324,9 +375,9 @@ class FLStyleSim:
         self.bank = ClientBank(abi.ARCH_D_2D if d == 2 else abi.ARCH_D_MNIST1, self.C, self.B, device=self.device,
                                loss_kind=abi.LOSS_BCE, lr=k.lr_d, b1=k.b1, b2=k.b2)
         n_total = k.num_workers if comm is None else k.num_workers * comm.world
-        # p[key] += paras[key] / len(client_list)  (flgan.py:151-158); weights override = FeGAN's softmax(sk)
-        self.w = (torch.full((self.C,), 1.0 / n_total) if weights is None else
-                  torch.as_tensor(weights, dtype=torch.float32)).to(self.device)
+        self.n_total = n_total
+        # p[key] += paras[key] / len(client_list)  (flgan.py:151-158): cgl_wsum_div; weights override = FeGAN's softmax(sk)
+        self.w = None if weights is None else torch.as_tensor(weights, dtype=torch.float32).to(self.device)
         self.comm = comm
         self.t = 0
 
@@ -360,7 +411,13 @@ class FLStyleSim:
                 bufs.append((self.G.trunk.stats, self.G.trunk.lay.ld_stats))
             for buf, ld in bufs:
                 g = torch.empty(ld, device=self.device)
-                _wsum(self.w, None, buf, ld, g, self.comm)
+                if self.w is not None:
+                    _wsum(self.w, None, buf, ld, g, self.comm)
+                else:       # every term divided by the client count, summed in client order (bit-exact on one GPU)
+                    abi.check(abi.lib.cgl_wsum_div(self.C, ld, float(self.n_total), 0, None, abi.ptr(buf), ld, abi.ptr(g),
+                                                   _stream()))
+                    if self.comm is not None:
+                        self.comm.allreduce_(g)
                 _bcast(None, 0.0, g, buf, ld, rows_n=self.C)
         self.t += 1
 

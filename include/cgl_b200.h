@@ -187,6 +187,15 @@ int cgl_wsum(int C, int64_t n, const float* w, const int32_t* rows, const float*
              float* out, cgl_stream_t stream);
 int cgl_bcast_mix(int R, int64_t n, const int32_t* rows, float sigma, const float* g, float* dst,
                   int64_t ld_dst, cgl_stream_t stream);
+/* The same sums where the reference DIVIDES instead of multiplying by a pre-computed share (bit-exact for counts that
+ * are not powers of two):
+ *   sum_first == 0: out[:] = sum_c (src[row(c), :] / divisor)     FL Server.run, `p[key] += paras[key] / len(client_list)`
+ *                                                                  (FLGAN/MNIST/flgan.py:151-158, FLGAN/2DMG/flgan.py:149-156)
+ *   sum_first != 0: out[:] = (sum_c src[row(c), :]) / divisor     receive_parameter (CGLGAN/2DMG/main.py:171-179)
+ * cgl_mix_csr with vals == NULL computes the second form per output row (divisor = the row's column count): the
+ * neighbour / group mean of discriminators.                                                                   */
+int cgl_wsum_div(int C, int64_t n, float divisor, int sum_first, const int32_t* rows, const float* src,
+                 int64_t ld_src, float* out, cgl_stream_t stream);
 
 /* ---- data side path kept on the GPU ----------------------------------
  * cgl_gather_rows: out[i,:] = data[idx[i],:] (idx[i] < 0: a row of zeros = the padding of a short last batch).

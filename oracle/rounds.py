@@ -17,12 +17,14 @@ from . import steps as st
 
 class OracleMD:
     def __init__(self, algo, num_workers, num_servers, batch_size, img_shape, iid=1, part_sizes=None,
-                 segema=0.0, cloud_epoch=1, cloud_mode="intended", lr=0.0002, b1=0.5, b2=0.999, weights_init=False):
+                 segema=0.0, cloud_epoch=1, cloud_mode="intended", lr=0.0002, b1=0.5, b2=0.999, weights_init=False,
+                 num_communication=20000, E=0, d_share="group_mean"):
         self.algo = algo
         self.S, self.N = num_servers, num_workers // num_servers
         self.C = self.S * self.N
         self.B = batch_size
         self.segema, self.cloud_epoch, self.cloud_mode = segema, cloud_epoch, cloud_mode
+        self.num_communication, self.E, self.d_share = num_communication, E, d_share
         d = 1
         for s in img_shape:
             d *= s
@@ -86,11 +88,43 @@ class OracleMD:
             recv = st.segema_mix(self_ps[s], {k: v.clone() for k, v in p.items()}, self.segema)
             g.model.load_state_dict(recv, strict=False)   # the intended target of main.py:208
 
+    def share(self):
+        """Neighbour-D share (commented out as shipped, README.md:26 "cancel the note to test").
+        swap      : MDGAN/MNIST/mdgan.py:158-164,258-262 -- the server collects its clients' D dicts in client order,
+                    self.rd.shuffle(p_ds) (Random(rank + 100), :122-123), client idx loads p_ds[idx].
+        group_mean: ACGAN/MNIST/acgan.py:240-263 -- w <- p; s <- mean of the group's w; p += s - w, i.e. every client of the
+                    server's group ends with the uniform mean (== the dead receive_parameter of CGLGAN/2DMG/main.py:171-179)."""
+        import random
+        if not hasattr(self, "rd"):
+            self.rd = [random.Random(s + 100) for s in range(self.S)]
+        N = self.N
+        for s in range(self.S):
+            cl = list(range(s * N, (s + 1) * N))
+            dicts = [st.copy_parameters(self.net_d[c]) for c in cl]
+            if self.d_share == "swap":
+                p_ds = st.mdgan_swap(dicts, self.rd[s])
+                for j, c in enumerate(cl):
+                    self.net_d[c].load_state_dict(p_ds[j], strict=False)
+            else:
+                mean = st.group_mean(dicts)
+                for c in cl:
+                    self.net_d[c].load_state_dict({k: v.clone() for k, v in mean.items()}, strict=False)
+
     def round(self, real, n_real, z_d, z_g):
         """real [epoch, C, B, d], n_real [epoch, C], z_d / z_g [S, B, 100]. Returns client G losses [S, N]."""
         S, N, B = self.S, self.N, self.B
-        if self.cloud_epoch and self.t % self.cloud_epoch == 0:
-            self.cloud()
+        t = self.num_communication - self.t          # the reference's counter counts down (while t > 0: ...; t -= 1)
+        if self.cloud_epoch:
+            if self.algo == "capgan":                # capgan.py:169: t % (self.data_len * cloud_epoch / batch_size) == 0
+                due = [bool(t % (self.data_len[s] * self.cloud_epoch / self.B) == 0) for s in range(S)]
+                assert all(due) or not any(due), "the reference's Cloud rendezvous would deadlock"
+                if all(due):
+                    self.cloud()
+            elif t % self.cloud_epoch == 0:          # CGLGAN/2DMG/main.py:201, mixed-gan.py:193, CAPGAN/MNIST/capgan.py:169
+                self.cloud()
+        # MDGAN/MNIST/mdgan.py:158,258: `if t % E == 0`; ACGAN/MNIST/acgan.py:240: `if (num_communication - t) % E == 0`
+        if self.E and ((self.t % self.E == 0) if self.algo == "acgan" else (t % self.E == 0)):
+            self.share()
         out = torch.zeros(S, N)
         for s in range(S):
             g = self.net_g[s]
