@@ -76,6 +76,10 @@ lib.cgl_mlp_workspace_bytes.restype = _sz
 lib.cgl_mlp_forward.argtypes = [C.POINTER(MlpDesc), _i32, _p, _i64, _p, _p, _i64, _i32, _p, _i64, _p, _i32, _p, _p, _sz, _p]
 lib.cgl_mlp_backward.argtypes = [C.POINTER(MlpDesc), _i32, _p, _p, _p, _i64, _p, _p, C.POINTER(TrainCfg), _p, _i64, _p,
                                  _i32, _p, _p, _p, _p, _sz, _p]
+lib.cgl_fl_step_workspace_bytes.argtypes = [C.POINTER(MlpDesc), C.POINTER(MlpDesc), _i32, _i32]
+lib.cgl_fl_step_workspace_bytes.restype = _sz
+lib.cgl_fl_step.argtypes = [C.POINTER(MlpDesc), C.POINTER(MlpDesc), _i32, _p, _p, _p, _i64, _p, _p, _i64, _p, _p, _p, _i64, _p,
+                            _p, _p, _p, _p, _p, _i32, C.POINTER(TrainCfg), C.POINTER(TrainCfg), _p, _p, _p, _sz, _p]
 lib.cgl_profile_enable.argtypes = [_i32]
 lib.cgl_profile_tag_name.argtypes = [_i32]
 lib.cgl_profile_tag_name.restype = C.c_char_p
@@ -95,7 +99,7 @@ lib.cgl_linear_bwd_data.argtypes = [_i32, _i32, _i32, _i32, _p, _i64, _p, _i64, 
 lib.cgl_linear_wgrad.argtypes = [_i32, _i32, _i32, _i32, _p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _p]
 
 for _name in ("cgl_arch_describe", "cgl_mlp_layout_of", "cgl_d_step", "cgl_g_loss", "cgl_dxg_reduce",
-              "cgl_adam_rows", "cgl_mix_csr", "cgl_wsum", "cgl_bcast_mix", "cgl_wsum_div", "cgl_comm_unique_id",
+              "cgl_adam_rows", "cgl_mix_csr", "cgl_wsum", "cgl_bcast_mix", "cgl_wsum_div", "cgl_fl_step", "cgl_comm_unique_id",
               "cgl_comm_init", "cgl_comm_destroy", "cgl_allreduce_sum", "cgl_mix_allreduce",
               "cgl_linear_fwd", "cgl_linear_bwd_data", "cgl_linear_wgrad", "cgl_set_gemm_mode", "cgl_mlp_forward", "cgl_mlp_backward", "cgl_profile_enable",
               "cgl_profile_summary", "cgl_debug_set_timeline", "cgl_linear_wgrad_adam", "cgl_gather_rows", "cgl_hist2d",

@@ -80,6 +80,14 @@ class ResidentPartitions:
                                           abi.ptr(out), _stream()))
         return out, n_dev
 
+    def gather(self, idx):
+        """[n, B] row ids on the host (-1 = padding) -> [n, B, d] on the device (cgl_gather_rows)."""
+        idx_dev = idx.contiguous().to(self.device, non_blocking=False)
+        out = torch.empty(idx.shape[0], idx.shape[1], self.d, device=self.device)
+        abi.check(abi.lib.cgl_gather_rows(idx.numel(), self.d, abi.ptr(self.data), self.n, abi.ptr(idx_dev), abi.ptr(out),
+                                          _stream()))
+        return out
+
     @property
     def h2d_bytes_per_round(self):
         return self.C * self.B * 8 + self.C * 4

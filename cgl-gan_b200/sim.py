@@ -14,7 +14,8 @@ The reference runs one Python thread per Worker / Server / Cloud and moves tenso
 
 Knob names are the reference's module-level globals (README.md:23-35).
 """
-from dataclasses import dataclass, field
+import ctypes
+from dataclasses import dataclass, field, replace
 from random import Random
 from typing import Optional
 
@@ -272,7 +273,7 @@ class MDStyleSim:
         kind = self.weighting
         if kind == "mean":                      # MDGAN/MNIST/mdgan.py:203, ACGAN/MNIST/acgan.py:173
             self.last_F_max = loss.mean(1)
-            return torch.full_like(loss, 1.0 / self.N)
+            return torch.full_like(loss, 1.0 / loss.shape[1])
         if kind == "cgl":                       # CGLGAN/2DMG/main.py:261-274
             gamma = F.softmax(Lam.unsqueeze(1) * loss, dim=1)
             F_beta = (beta * loss).sum(1)
@@ -343,6 +344,101 @@ class MDStyleSim:
             self.bank.mix((row_ptr, col, None))                         # row means (sum, then one division)
 
 
+class MDSingleServerSim(MDStyleSim):
+    """ONE edge server whose clients are dealt over the ranks -- MD-GAN as shipped (MDGAN/MNIST/mdgan.py:35-36:
+    num_servers = 1) on several GPUs. Every rank keeps a replica of the generator and the discriminators of its
+    own block of clients; per round the ranks exchange
+      * the clients' G losses (all-gather of N floats: the weighting of SURVEY 3.4 needs all of them), and
+      * sum_i w_i dLoss_i/dXg, the gradient of the server objective with respect to the shared batch Xg ([B, d] floats,
+        one all-reduce over NVLink) -- what F_max.backward() accumulates into Xg in the reference (mdgan.py:203-204),
+    and every rank takes the identical generator step (same kernels, same inputs: the replicas stay bit-identical).
+    z_d / z_g must be the same on every rank (default: a device generator seeded alike on all ranks).
+    Single-path generators only (mdgan, acgan, capgan, capgan_copy, cglgan with iid == 0)."""
+
+    def __init__(self, algo, knobs: Knobs, part_sizes=None, device="cuda", comm=None, rank=0, world=1, z_seed=20211212):
+        from .dist import shard_range
+        assert knobs.num_servers == 1, "MDSingleServerSim shards the clients of ONE server"
+        self.N_total = knobs.num_workers
+        self.rank, self.world = rank, world
+        self.lo, self.hi = shard_range(self.N_total, world, rank)
+        assert (self.hi - self.lo) * world == self.N_total, "the clients must divide evenly over the ranks (all-gather of the losses)"
+        sizes = [1] * self.N_total if part_sizes is None else list(part_sizes)
+        local = replace(knobs, num_workers=self.hi - self.lo)
+        super().__init__(algo, local, part_sizes=sizes[self.lo:self.hi], device=device, comm=None)
+        assert not self.multi_head, "one head per client would shard the generator itself: single-path generators only"
+        self.xcomm = comm                                   # dist.ShardComm (None: one rank)
+        full = torch.tensor(sizes, dtype=torch.float32).view(1, self.N_total)
+        self.data_len = full.sum(1)
+        self.beta = (full / self.data_len.unsqueeze(1)).to(self.device)      # shares over ALL clients of the server
+        self.A = torch.ones(1, device=self.device)
+        self._zgen = torch.Generator(device=self.device)
+        self._zgen.manual_seed(z_seed)
+
+    def round(self, real, n_real=None, z_d=None, z_g=None):
+        """real [epoch, N_local, B, d] (this rank's clients). Returns the G losses of ALL clients [1, N_total]."""
+        import torch.distributed as dist
+        k, B, d = self.k, self.B, self.d
+        if real.dim() == 3:
+            real = real.unsqueeze(0)
+        if n_real is not None and n_real.dim() == 1:
+            n_real = n_real.unsqueeze(0)
+        if self._share_due():
+            self.share_discriminators()
+        if z_d is None:
+            z_d = torch.randn(1, B, 100, device=self.device, generator=self._zgen)
+        if z_g is None:
+            z_g = torch.randn(1, B, 100, device=self.device, generator=self._zgen)
+        G = self.G
+        Xd = G(z_d).reshape(1, B, d)
+        Xg = G(z_g).reshape(1, B, d)
+        for e in range(real.shape[0]):
+            self.last_d_loss = self.bank.d_step(real[e], Xd, n_real=None if n_real is None else n_real[e],
+                                                fake_idx=self.server_of)
+        loss_local, dxg = self.bank.g_loss_raw(Xg, xg_idx=self.server_of)
+        if self.world > 1:
+            loss = torch.empty(self.N_total, device=self.device)
+            dist.all_gather_into_tensor(loss, loss_local.contiguous())
+        else:
+            loss = loss_local
+        loss = loss.view(1, self.N_total)
+        w = self._server_weights(loss)                      # identical on every rank (replicated Lambda, all losses)
+        w_local = w[0, self.lo:self.hi].contiguous().float()
+        dy = torch.empty(1, B, d, device=self.device)
+        abi.check(abi.lib.cgl_dxg_reduce(1, abi.ptr(self.srv_ptr), None, abi.ptr(w_local), abi.ptr(dxg), B * d, abi.ptr(dy),
+                                         _stream()))
+        if self.xcomm is not None:
+            self.xcomm.allreduce_(dy)                       # the one data-path collective: [B, d] floats
+        G.backward_step(dy.view(1, 1, B, d) if self.n_heads else dy)
+        self.t += 1
+        return loss
+
+    def _cloud_due(self):
+        return False    # a single server: the Cloud average of one generator is that generator
+
+    def share_discriminators(self):
+        """swap: the server's shuffle runs over ALL its clients (same seeded generator on every rank), every rank
+        all-gathers the discriminator rows and keeps the ones dealt to its clients; group mean: local sum, all-reduce,
+        one division (the order of the additions differs from the single-process loop by the partial sums)."""
+        import torch.distributed as dist
+        bank, N = self.bank, self.N_total
+        if self.k.d_share == "swap":
+            order = list(range(N))
+            self.swap_rd[0].shuffle(order)
+            if self.world > 1:
+                full = torch.empty(N, bank.ld, device=self.device)
+                dist.all_gather_into_tensor(full, bank.params.contiguous())
+            else:
+                full = bank.params.clone()
+            take = torch.tensor(order[self.lo:self.hi], device=self.device, dtype=torch.long)
+            bank.params.copy_(full.index_select(0, take))
+        else:
+            g = torch.empty(bank.ld, device=self.device)
+            ones = torch.ones(bank.C, device=self.device)
+            _wsum(ones, None, bank.params, bank.ld, g, self.xcomm)
+            g.div_(float(N))
+            _bcast(None, 0.0, g, bank.params, bank.ld, rows_n=bank.C)
+
+
 def _wsum(w, rows, buf, ld, out, comm):
     w = w.contiguous()
     if comm is None:
@@ -380,6 +476,7 @@ class FLStyleSim:
         self.w = None if weights is None else torch.as_tensor(weights, dtype=torch.float32).to(self.device)
         self.comm = comm
         self.t = 0
+        self._ws = None
 
     def load_global(self, g_module, d_module):
         """Round-0 state: the server's initial net_g / net_d copied to every client (flgan.py:139-146)."""
@@ -388,19 +485,60 @@ class FLStyleSim:
 
     def local_minibatch(self, real, n_real=None, z_d=None, z_g=None, client_ids=None):
         """One D step + one G step on every client (flgan.py:251-269), or on the clients listed in client_ids
-        (int32 device tensor: FeGAN's group of the round; real / z then hold one entry per listed client)."""
-        C, B = (self.C if client_ids is None else client_ids.numel()), self.B
+        (int32 device tensor: FeGAN's group of the round; real / z then hold one entry per listed client).
+        One call of the C ABI: cgl_fl_step."""
+        C_, B = (self.C if client_ids is None else client_ids.numel()), self.B
+        if C_ == 0:
+            return torch.empty(0, device=self.device), torch.empty(0, device=self.device)
         if z_d is None:
-            z_d = torch.randn(C, B, 100, device=self.device)
+            z_d = torch.randn(C_, B, 100, device=self.device)
         if z_g is None:
-            z_g = torch.randn(C, B, 100, device=self.device)
-        G = self.G
-        Xd = G(z_d, ids=client_ids)   # the G grads D_loss.backward() leaves behind are zeroed at flgan.py:264: a plain forward
-        d_loss = self.bank.d_step(real, Xd.reshape(C, B, self.d), n_real=n_real, client_ids=client_ids)
-        Xg = G(z_g, ids=client_ids)
-        g_loss, dxg = self.bank.g_loss_raw(Xg.reshape(C, B, self.d), client_ids=client_ids)
-        G.backward_step(dxg)     # g_loss.backward(); opti_g.step()  (flgan.py:266-269)
+            z_g = torch.randn(C_, B, 100, device=self.device)
+        G, bank = self.G, self.bank
+        tb = G.trunk
+        ids = None if client_ids is None else client_ids.to(device=self.device, dtype=torch.int32).contiguous()
+        z_d = z_d.reshape(C_, B, 100).contiguous().float()
+        z_g = z_g.reshape(C_, B, 100).contiguous().float()
+        real = real.reshape(C_, B, self.d).contiguous()
+        n_real = None if n_real is None else n_real.to(device=self.device, dtype=torch.int32).contiguous()
+        nbytes = abi.lib.cgl_fl_step_workspace_bytes(ctypes.byref(tb.desc), ctypes.byref(bank.desc), C_, B)
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        d_loss, g_loss = torch.empty(C_, device=self.device), torch.empty(C_, device=self.device)
+        abi.check(abi.lib.cgl_fl_step(
+            ctypes.byref(tb.desc), ctypes.byref(bank.desc), C_, abi.ptr(tb.params), abi.ptr(tb.adam_m), abi.ptr(tb.adam_v),
+            tb.lay.ld, abi.ptr(tb.step), abi.ptr(tb.stats), tb.lay.ld_stats, abi.ptr(bank.params), abi.ptr(bank.adam_m),
+            abi.ptr(bank.adam_v), bank.ld, abi.ptr(bank.step), abi.ptr(ids), abi.ptr(z_d), abi.ptr(z_g), abi.ptr(real),
+            abi.ptr(n_real), B, ctypes.byref(bank.cfg), ctypes.byref(G.cfg), abi.ptr(d_loss), abi.ptr(g_loss),
+            abi.ptr(self._ws), self._ws.numel(), _stream()))
         return d_loss, g_loss
+
+    def local_epochs(self, parts, epoch=1, z_fn=None, client_ids=None):
+        """FL Worker.train as the MNIST scripts run it (FLGAN/MNIST/flgan.py:249-250, fegan.py:282-283): `epoch` FULL passes
+        `for imgs in DataLoader(dataset, batch_size)` over the client's own partition, unshuffled, the last batch short.
+        parts: data.ResidentPartitions (the dataset resident in HBM, one list of row ids per client). Clients with fewer
+        batches simply stop earlier: minibatch j runs on the clients that still have a j-th batch.
+        z_fn(n) -> (z_d, z_g) [n, B, 100] injects the noise (default: torch.randn on the device).
+        Returns the number of client-minibatches done."""
+        ids_all = list(range(self.C)) if client_ids is None else [int(c) for c in client_ids]
+        B = self.B
+        nb = {c: (len(parts.parts[c]) + B - 1) // B for c in ids_all}
+        done = 0
+        for _ in range(epoch):
+            for j in range(max(nb.values()) if nb else 0):
+                active = [c for c in ids_all if nb[c] > j]
+                idx = torch.full((len(active), B), -1, dtype=torch.int64)
+                n = torch.empty(len(active), dtype=torch.int32)
+                for a, c in enumerate(active):
+                    rows = parts.parts[c][j * B:(j + 1) * B]
+                    idx[a, :rows.numel()] = rows
+                    n[a] = rows.numel()
+                real = parts.gather(idx)
+                z_d, z_g = z_fn(len(active)) if z_fn else (None, None)
+                cid = None if len(active) == self.C and client_ids is None else torch.tensor(active, dtype=torch.int32)
+                self.local_minibatch(real, n.to(self.device), z_d, z_g, client_ids=cid)
+                done += len(active)
+        return done
 
     def aggregate(self):
         """Server.run: uniform (or weighted) average of every client's G and D, loaded back into every
@@ -427,10 +565,21 @@ class FeGANSim(FLStyleSim):
     the population) receives the global G and D -- parameters only: SerializationTool.deserialize_model leaves
     BatchNorm running statistics and the Adam state with the client -- trains locally like an FL-GAN client, and
     the server replaces the global vectors by fedavg_aggregate over the group with weights softmax(sk), sk the
-    clients' KL scores (fegan.py:142-146,163-164)."""
+    clients' KL scores (fegan.py:142-146,163-164).
 
-    def __init__(self, knobs, sk, groups, device="cuda"):
-        super().__init__(knobs, device=device)
+    Several GPUs (comm given): the POPULATION is dealt over the ranks in contiguous blocks -- a client's Adam moments and
+    BatchNorm statistics persist between the rounds it takes part in, so its state stays with its owner -- and a round's
+    group is served by the owners of its members: no client state ever moves. The only exchange is the all-reduce of the two
+    weighted partial sums (weights normalised over the WHOLE group), after which every rank holds the new global vectors.
+    `knobs.num_workers` is the population size; ids / real / z of a round are those of the members this rank owns."""
+
+    def __init__(self, knobs, sk, groups, device="cuda", comm=None, rank=0, world=1):
+        from .dist import shard_range
+        self.N_pop = knobs.num_workers
+        self.rank, self.world = rank, world
+        self.lo, self.hi = shard_range(self.N_pop, world, rank)
+        super().__init__(replace(knobs, num_workers=self.hi - self.lo), device=device)
+        self.xcomm = comm
         self.sk = torch.as_tensor(sk, dtype=torch.float32)
         self.groups = [list(g) for g in groups]
         self.p_g = torch.zeros(self.G.trunk.lay.ld, device=self.device)
@@ -446,16 +595,28 @@ class FeGANSim(FLStyleSim):
         self.p_d[:fd.numel()].copy_(fd)
 
     def begin_round(self):
-        """-> (group, ids): the round's clients; the global vectors are loaded into their rows."""
+        """-> (members, ids): the members of the round's group this rank owns (global client numbers, in group order) and
+        their local rows; the global vectors are loaded into those rows."""
         group = self.groups[self.t % len(self.groups)]
-        ids = torch.tensor(group, dtype=torch.int32, device=self.device)
-        _bcast(ids, 0.0, self.p_d, self.bank.params, self.bank.ld)
-        _bcast(ids, 0.0, self.p_g, self.G.trunk.params, self.G.trunk.lay.ld)
-        return group, ids
+        mine = [c for c in group if self.lo <= c < self.hi]
+        ids = torch.tensor([c - self.lo for c in mine], dtype=torch.int32, device=self.device)
+        if mine:
+            _bcast(ids, 0.0, self.p_d, self.bank.params, self.bank.ld)
+            _bcast(ids, 0.0, self.p_g, self.G.trunk.params, self.G.trunk.lay.ld)
+        return mine, ids
 
-    def end_round(self, group, ids):
-        w = torch.exp(self.sk[group])                  # weight = exp(sk); weight /= weight.sum()
-        w = (w / w.sum()).to(self.device)
-        _wsum(w, ids, self.bank.params, self.bank.ld, self.p_d, None)
-        _wsum(w, ids, self.G.trunk.params.detach(), self.G.trunk.lay.ld, self.p_g, None)
+    def end_round(self, mine, ids):
+        group = self.groups[self.t % len(self.groups)]
+        w_all = torch.exp(self.sk[group])                  # weight = exp(sk); weight /= weight.sum()  (over the whole group)
+        w_all = w_all / w_all.sum()
+        pos = {c: j for j, c in enumerate(group)}
+        w = w_all[[pos[c] for c in mine]].to(self.device) if mine else torch.zeros(0, device=self.device)
+        for buf, ld, out in ((self.bank.params, self.bank.ld, self.p_d),
+                             (self.G.trunk.params.detach(), self.G.trunk.lay.ld, self.p_g)):
+            if mine:
+                _wsum(w, ids, buf, ld, out, None)
+            else:
+                out.zero_()
+            if self.xcomm is not None:
+                self.xcomm.allreduce_(out)
         self.t += 1

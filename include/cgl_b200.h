@@ -164,6 +164,22 @@ int cgl_mlp_backward(const cgl_mlp_desc* arch, int G, float* params, float* adam
                      const float* x, int64_t x_gstride, const int32_t* x_idx, int rows, const float* y,
                      const float* dy, float* dx, void* workspace, size_t workspace_bytes, cgl_stream_t stream);
 
+/* ---- one FL-style local minibatch in one call (a5) -------------------------------------------------------
+ * Replaces the body of FL Worker.train's minibatch loop, FLGAN/MNIST/flgan.py:251-269, FLGAN/2DMG/flgan.py:239-256,
+ * fegan.py:284-303, for G clients that each own a generator (arch_g, BatchNorm statistics in g_bn_stats) and a
+ * discriminator (arch_d):   Xd = G(z_d);  D step on (real, Xd) [cgl_d_step];  Xg = G(z_g);  g_loss = loss(D(Xg), valid);
+ *                           g_loss.backward();  opti_g.step() [cgl_mlp_backward].
+ * ids (NULL: identity) picks the rows of BOTH banks (FeGAN's group of the round). z_d / z_g are [G, B, arch_g->dims[0]],
+ * real is [G, B, d] with n_real valid rows. Every intermediate batch stays in `workspace`
+ * (cgl_fl_step_workspace_bytes). out_dloss / out_gloss: [G].                                                   */
+size_t cgl_fl_step_workspace_bytes(const cgl_mlp_desc* arch_g, const cgl_mlp_desc* arch_d, int G, int B);
+int cgl_fl_step(const cgl_mlp_desc* arch_g, const cgl_mlp_desc* arch_d, int G, float* g_params, float* g_adam_m,
+                float* g_adam_v, int64_t ld_g, int32_t* g_step, float* g_bn_stats, int64_t ld_stats, float* d_params,
+                float* d_adam_m, float* d_adam_v, int64_t ld_d, int32_t* d_step, const int32_t* ids, const float* z_d,
+                const float* z_g, const float* real, const int32_t* n_real, int B, const cgl_train_cfg* cfg_d,
+                const cgl_train_cfg* cfg_g, float* out_dloss, float* out_gloss, void* workspace, size_t workspace_bytes,
+                cgl_stream_t stream);
+
 /* ---- fused Adam over packed rows (server-side G, a7) ------------------------------------
  * torch.optim.Adam(betas=(b1,b2)) semantics, CGLGAN/2DMG/main.py:192. step[r] is incremented.
  * rows: R rows of n floats, `ld` floats apart, for p / g / m / v alike.                      */

@@ -78,23 +78,24 @@ def assert_params_close(a, b, lr=2e-4, steps=1, tag="", strict=True, bulk=1e-5):
         assert no <= max(2, 1e-3 * a.numel()), (tag, "elements outside 1e-5", no, a.numel())
 
 
-def assert_rows_close(a, b, tag="", row_frac=0.97, tol=1e-5):
-    """Activation-gradient tensors [rows, width] (dLoss/dXg): >= 97 % of the rows within 1e-5 of the
-    tensor's scale; a row may differ where a LeakyReLU pre-activation of that sample sits on the kink
-    (one flipped unit of the 256-wide layer moves that sample's row by ~8 %, i.e. ~1 % of the batch's L2)."""
+def assert_rows_close(a, b, tag="", row_frac=0.99, tol=1e-5):
+    """Activation-gradient tensors [rows, width] (dLoss/dXg): >= 99 % of the rows (all but one of a batch of 100)
+    within 1e-5 of the tensor's scale; a row may differ where a LeakyReLU pre-activation of that sample sits on the
+    kink (one flipped unit of the 256-wide layer moves that sample's row by ~8 %, i.e. ~1 % of the batch's L2).
+    Measured on B200 (profiles/parity_r2.json, dXg_probe after one round): max-norm <= 8.1e-6, q99 <= 5.5e-7."""
     a, b = a.detach().double().cpu(), b.detach().double().cpu()
     a, b = a.reshape(-1, a.shape[-1]), b.reshape(-1, b.shape[-1])
     row_err = (a - b).abs().max(dim=1).values / b.abs().max().clamp_min(1e-30)
     ok = (row_err <= tol).double().mean().item()
     assert ok >= row_frac, (tag, "rows within tol", tol, ok)
-    assert rel_l2(a, b) < 5e-2, (tag, "rel_l2", rel_l2(a, b))
+    assert rel_l2(a, b) < 2e-2, (tag, "rel_l2", rel_l2(a, b))
 
 
-def assert_grad_close(a, b, tag="", tol=1e-4, elem_frac=0.99, l2=2e-2):
+def assert_grad_close(a, b, tag="", tol=2e-5, elem_frac=0.99, l2=1e-2):
     """dLoss/dXg AFTER Adam steps: the two discriminators differ at the ill-conditioned elements (see
     assert_params_close). One flipped first-layer weight moves a whole COLUMN of dLoss/dXg, one LeakyReLU kink
-    flip a whole ROW; everything else agrees to fp32 rounding. So: >= 99 % of the elements within 1e-4 of the
-    tensor's scale, and a bounded L2 distance."""
+    flip a whole ROW; everything else agrees to fp32 rounding. So: >= 99 % of the elements within 2e-5 of the
+    tensor's scale (measured after one round: max-norm <= 8.1e-6, profiles/parity_r2.json), and a bounded L2 distance."""
     a, b = a.detach().double().cpu(), b.detach().double().cpu()
     ok = ((a - b).abs() <= tol * b.abs().max().clamp_min(1e-30)).double().mean().item()
     assert ok >= elem_frac, (tag, "elements within tol", tol, ok)

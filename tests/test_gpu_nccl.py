@@ -21,3 +21,17 @@ def test_sharded_round_over_nccl_matches_single_process(lib):
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert "NCCL_CHECK ok" in res.stdout
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_sharded_mdgan_fegan_flgan_over_nccl_match_single_process(lib):
+    """Single-server MD-GAN with its clients dealt over the ranks (replicated generator, all-reduce of the weighted
+    dLoss/dXg), FeGAN with the population dealt over the ranks, FL-GAN rounds over a communicator: each against the same
+    simulation in one process (tests/nccl_sharded_algos_check.py)."""
+    world = 2
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(29900 + os.getpid() % 90),
+           os.path.join(ROOT, "tests", "nccl_sharded_algos_check.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert "NCCL_ALGOS ok" in res.stdout

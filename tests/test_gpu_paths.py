@@ -242,3 +242,72 @@ def test_discriminator_sharing_inside_a_round(lib, d_share, algo):
     for c in range(W):
         ref = torch.cat([p.detach().reshape(-1) for p in orc.net_d[c].parameters()])
         assert_params_close(sim.bank.rows()[c], ref, steps=4, tag=(d_share, c), strict=False, bulk=1e-4)
+
+
+def test_single_server_sharded_sim_on_one_rank_is_the_plain_sim(lib):
+    """sim.MDSingleServerSim with world = 1 (no collective) is bit-identical to MDStyleSim with one server."""
+    from cgl_gan_b200 import models
+    from cgl_gan_b200.sim import Knobs, MDSingleServerSim, MDStyleSim
+    torch.manual_seed(17)
+    W, B, shape, d = 5, 100, (1, 28, 28), 784
+    sizes = [300 + 41 * i for i in range(W)]
+    k = Knobs(num_workers=W, num_servers=1, batch_size=B, img_shape=shape)
+    a = MDStyleSim("mdgan", k, part_sizes=sizes)
+    b = MDSingleServerSim("mdgan", k, part_sizes=sizes)
+    g_mod = a.G.make_module()
+    d_mods = [models.Discriminator(shape) for _ in range(W)]
+    a.load([g_mod], d_mods)
+    b.load([g_mod], d_mods)
+    for r in range(2):
+        real, n_real, z_d, z_g = _round_inputs(W, 1, B, d, 300 + r)
+        la = a.round(real.cuda(), n_real.cuda(), z_d.cuda(), z_g.cuda())
+        lb = b.round(real.cuda(), n_real.cuda(), z_d.cuda(), z_g.cuda())
+        assert torch.equal(la, lb)
+    assert torch.equal(a.bank.params, b.bank.params) and torch.equal(a.G.trunk.params, b.G.trunk.params)
+
+
+def test_fl_local_epochs_are_full_unshuffled_passes(lib):
+    """FLGAN-MNIST / FeGAN Worker.train: `epoch` full passes `for imgs in DataLoader(dataset, batch_size)` over the
+    client's partition (FLGAN/MNIST/flgan.py:249-250); partitions of different sizes, short last batches."""
+    from cgl_gan_b200.data import ResidentPartitions
+    from cgl_gan_b200.sim import FLStyleSim, Knobs
+    from oracle.rounds import OracleFL
+    torch.manual_seed(23)
+    C_, B, shape, d = 3, 100, (2,), 2
+    data = torch.tanh(torch.randn(700, d))
+    parts = [list(range(0, 250)), list(range(250, 330)), list(range(330, 700))]      # 3, 1 and 4 batches
+    orc = OracleFL(C_, B, shape)
+    orc.load_global()
+    sim = FLStyleSim(Knobs(num_workers=C_, num_servers=1, batch_size=B, img_shape=shape))
+    sim.load_global(orc.srv_g, orc.srv_d)
+    rp = ResidentPartitions(data, parts, B, shuffle=False)
+    gen = torch.Generator().manual_seed(4)
+    zs = []
+
+    def z_fn(n):
+        z = (torch.randn(n, B, 100, generator=gen), torch.randn(n, B, 100, generator=gen))
+        zs.append(z)
+        return z[0].cuda(), z[1].cuda()
+
+    done = sim.local_epochs(rp, epoch=2, z_fn=z_fn)
+    assert done == 2 * (3 + 1 + 4)
+    # the oracle: per client its own DataLoader loop, fed the noise the engine drew for that (minibatch, client)
+    nb = [3, 1, 4]
+    it = iter(zs)
+    per_client = {c: [] for c in range(C_)}
+    for _ in range(2):
+        for j in range(max(nb)):
+            z_d, z_g = next(it)
+            active = [c for c in range(C_) if nb[c] > j]
+            for a, c in enumerate(active):
+                per_client[c].append((j, z_d[a], z_g[a]))
+    from oracle import steps as st
+    loss = st.make_loss(0)
+    for c in range(C_):
+        rows = torch.tensor(parts[c])
+        for j, z_d, z_g in per_client[c]:
+            imgs = data[rows[j * B:(j + 1) * B]]
+            st.fl_local_minibatch(orc.net_d[c], orc.net_g[c], loss, orc.opti_g[c], orc.opti_d[c], imgs, z_d, z_g, B)
+        ref = torch.cat([p.detach().reshape(-1) for p in orc.net_d[c].parameters()])
+        assert_params_close(sim.bank.rows()[c], ref, steps=len(per_client[c]), tag=("D", c), strict=False, bulk=1e-4)
+    assert sim.bank.step.tolist() == [6, 2, 8]
