@@ -13,7 +13,6 @@ kl_score_2d: plot_2d's KL score (CGLGAN/2DMG/main.py:68-94) on the GPU.
 import ctypes as C
 
 import torch
-from torch.utils.data import DataLoader
 
 from . import abi
 from .engine import _stream
@@ -32,14 +31,45 @@ class ResidentPartitions:
         self.d = self.data.shape[1]
         self.parts = [torch.as_tensor(p, dtype=torch.int64) for p in partitions]
         self.C, self.B, self.shuffle = len(self.parts), int(batch_size), shuffle
-        # Worker.__init__: one DataLoader per client, created in client order (each iter() draws from the global RNG)
-        self.loaders = [DataLoader(dataset=p, batch_size=self.B, shuffle=shuffle) for p in self.parts]
-        self.iters = [iter(dl) for dl in self.loaders]
+        # Worker.__init__: one DataLoader per client and its iterator, created in client order. The host side keeps no
+        # DataLoader objects (1024 Python iterators cost ~80 ms per round, three times the round itself): it makes the
+        # same draws from torch's global RNG, in the same order, that DataLoader(shuffle=...) makes --
+        #   iter(DataLoader)         : _BaseDataLoaderIter draws its base seed        torch.empty((), int64).random_()
+        #   first next() of an epoch : RandomSampler draws its seed the same way and takes torch.randperm(n, generator)
+        # -- so the row ids are bit-identical to the reference's (tests/test_gpu_data.py checks them against real DataLoaders).
+        self._perm = [None] * self.C          # row ids of the running epoch in visiting order (None: not drawn yet)
+        self._cur = [0] * self.C
+        for _ in range(self.C):
+            self._draw_seed()                 # iter(self.dataloader) in Worker.__init__
         # A ring of pinned staging slots: the host runs ahead of the stream (a round enqueues dozens of kernels), so a
         # slot is rewritten only after the event recorded behind its previous host -> device copy has completed.
         self._slots = [dict(idx=torch.empty(self.C, self.B, dtype=torch.int64).pin_memory(),
                             n=torch.empty(self.C, dtype=torch.int32).pin_memory(), ev=None) for _ in range(STAGING_SLOTS)]
         self._slot = 0
+        self._ready = None
+
+    def prefetch(self):
+        """Draws the NEXT round's row ids now (host work only, the same draws in the same order): call it right after a
+        round was enqueued so that it runs while the GPU works; next_batches() then only ships them."""
+        if self._ready is None:
+            slot = self._slots[self._slot]
+            self._slot = (self._slot + 1) % len(self._slots)
+            self.next_indices(slot)
+            self._ready = slot
+
+    @staticmethod
+    def _draw_seed():
+        return int(torch.empty((), dtype=torch.int64).random_().item())
+
+    def _start_epoch(self, c):
+        part = self.parts[c]
+        if self.shuffle:
+            g = torch.Generator()
+            g.manual_seed(self._draw_seed())                       # RandomSampler.__iter__
+            self._perm[c] = part[torch.randperm(part.numel(), generator=g)]
+        else:
+            self._perm[c] = part                                   # SequentialSampler
+        self._cur[c] = 0
 
     def next_indices(self, slot=None):
         """One `next(self.data)` per client, in client order (Worker.train, main.py:350-355). Returns the pinned
@@ -53,23 +83,31 @@ class ResidentPartitions:
             slot["ev"] = None
         idx, n = slot["idx"], slot["n"]
         idx.fill_(-1)
+        B = self.B
         for c in range(self.C):
-            try:
-                rows = next(self.iters[c])
-            except StopIteration:
-                self.loaders[c] = DataLoader(dataset=self.parts[c], batch_size=self.B, shuffle=self.shuffle)
-                self.iters[c] = iter(self.loaders[c])
-                rows = next(self.iters[c])
+            perm = self._perm[c]
+            if perm is None:
+                self._start_epoch(c)                               # the first next() of the iterator made in __init__
+            elif self._cur[c] >= perm.numel():                     # StopIteration: a NEW DataLoader and iterator, then next()
+                self._draw_seed()
+                self._start_epoch(c)
+            perm, cur = self._perm[c], self._cur[c]
+            rows = perm[cur:cur + B]
             k = rows.numel()
             idx[c, :k] = rows
             n[c] = k
+            self._cur[c] = cur + k
         return idx, n
 
     def next_batches(self, out=None):
         """-> (real [C, B, d] on the device, n_real [C] int32 on the device) for MDStyleSim.round / FLStyleSim."""
-        slot = self._slots[self._slot]
-        self._slot = (self._slot + 1) % len(self._slots)
-        idx, n = self.next_indices(slot)
+        if self._ready is not None:
+            slot, self._ready = self._ready, None
+            idx, n = slot["idx"], slot["n"]
+        else:
+            slot = self._slots[self._slot]
+            self._slot = (self._slot + 1) % len(self._slots)
+            idx, n = self.next_indices(slot)
         idx_dev = idx.to(self.device, non_blocking=True)      # per-round device tensors: nothing aliases across rounds
         n_dev = n.to(self.device, non_blocking=True)
         slot["ev"] = torch.cuda.Event()
