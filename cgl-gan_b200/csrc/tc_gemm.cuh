@@ -54,11 +54,14 @@ constexpr int TC_THREADS = TC_LOADER_THREADS + 32;
 #ifndef TC_WG_STAGES
 #define TC_WG_STAGES 2   // its 32 KB stages (the Adam epilogue's transpose buffer needs 64 KB)
 #endif
+#ifndef TC_PF_BLOCKS
+#define TC_PF_BLOCKS 8    // distance (k-blocks) of the 512-byte row prefetches ahead of the operand loads (tune bit 2048)
+#endif
 #ifndef TC_LW16_DEPTH
 #define TC_LW16_DEPTH 3   // k-blocks of loads in flight per thread of the 16-loader-warp forward kernel
 #endif
 constexpr int TC_MAX_BN = 256;
-constexpr int TC_TUNE_DEFAULT = 1 | 8 | 32 | 64;
+constexpr int TC_TUNE_DEFAULT = 1 | 8 | 32 | 64 | 256 | 512 | 1024;
 constexpr uint32_t TC_WAIT_HINT_NS = 20000u;
 
 // ---- PTX wrappers ----------------------------------------------------------------------------
@@ -262,7 +265,12 @@ struct TcParams {
   int tune;  // bits (tc_tune()): 1 = L2 prefetch of the Adam tile under the main loop, 8 / 16 = persistent kernel
              // (tc_persist.cuh) for the data-gradient / forward product, 32 = 16 loader warps in the one-tile forward kernel,
              // 64 = 16-row stages (two of them) in the weight-gradient kernel, 128 = 16 loader warps in the one-tile
-             // data-gradient kernel (with 8 cleared; measured equal to the persistent kernel: 5.26 against 5.30 ms per round)
+             // data-gradient kernel (with 8 cleared; measured equal to the persistent kernel: 5.26 against 5.30 ms per round),
+             // 256 / 512 = CTA pairs (tc_pair.cuh, cta_group::2) for the forward / data-gradient product,
+             // 1024 = two CTAs per SM for short-K (<= 43 k-steps) forward / data-gradient products,
+             // 2048 = 512-byte row prefetches into L2, 4096 / 8192 = bring-up ablations (no global loads / no MMAs),
+             // 16384 / 32768 = persistent kernel with the lean 16-warp loader loop (tc_sweep.cuh) for forward / data gradient,
+             // 65536 = CTA pairs also for an odd number of M tiles
 };
 
 // TMEM plan (512 columns, 1 CTA per SM). The tensor core TRUNCATES when it adds into an fp32
@@ -367,9 +375,11 @@ __global__ void __launch_bounds__(LW * 32 + 32, OCC) tc_grouped_gemm_kernel(cons
             const uint64_t dbl = umma_desc(sb_lo + j * b_step, b_lbo, b_sbo, b_lay);
             const uint32_t main_col = (uint32_t)((1 + reg) * stride);
             if (++reg == n_main) reg = 0;
-            umma_tf32(tmem_d, dal, dbh, idesc, ks > 0 ? 1u : 0u);
-            umma_tf32(tmem_d, dah, dbl, idesc, 1u);
-            umma_tf32(tmem_d + main_col, dah, dbh, idesc, ks >= n_main ? 1u : 0u);
+            if (!(p.tune & 8192)) {   // (bring-up: 8192 = no MMAs, what the loop costs without the tensor core)
+              umma_tf32(tmem_d, dal, dbh, idesc, ks > 0 ? 1u : 0u);
+              umma_tf32(tmem_d, dah, dbl, idesc, 1u);
+              umma_tf32(tmem_d + main_col, dah, dbh, idesc, ks >= n_main ? 1u : 0u);
+            }
             ++ks;
           }
         }
@@ -407,6 +417,13 @@ __global__ void __launch_bounds__(LW * 32 + 32, OCC) tc_grouped_gemm_kernel(cons
     float4 ra[DEPTH][NA], rb[DEPTH][NBW];
     auto load_block = [&](int kb, float4 (&qa)[NA], float4 (&qb)[NBW]) {
       const int k0 = kb * BKT;
+      if (p.tune & 4096) {          // bring-up: no global loads at all (what the loop costs without the memory system)
+#pragma unroll
+        for (int i = 0; i < NA; ++i) qa[i] = make_float4(1.f, 2.f, 3.f, (float)kb);
+#pragma unroll
+        for (int i = 0; i < NBW; ++i) qb[i] = make_float4(1.f, 2.f, 3.f, (float)kb);
+        return;
+      }
 #pragma unroll
       for (int i = 0; i < NA; ++i) qa[i] = tc_patch_load<A_KMAJOR, BKT>(RA, warp + LW * i, lane, m0, p.M, k0, p.K);
 #pragma unroll
@@ -431,7 +448,9 @@ __global__ void __launch_bounds__(LW * 32 + 32, OCC) tc_grouped_gemm_kernel(cons
         const int pp = warp + LW * i;
         if (pp < npb) tc_split_store(b_hi, b_lo, tc_patch_offset<B_KMAJOR, BKT>(pp, lane), qb[i]);
       }
-      fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core (async proxy)
+      // generic-proxy stores -> visible to the tensor core (async proxy), then one arrival per thread. (One arrival per
+      // WARP after a __syncwarp was measured: 3 % slower -- the arrivals are not what the loop costs.)
+      fence_proxy_async_smem();
       mbar_arrive(smem_u32(&bar_full[st_s]));
       if (++st_s == nst) {
         st_s = 0;
@@ -457,6 +476,25 @@ __global__ void __launch_bounds__(LW * 32 + 32, OCC) tc_grouped_gemm_kernel(cons
       }
     };
     const int kb_prefetch = nkb > DEPTH ? nkb - DEPTH - 1 : 0;   // right after the last operand loads are issued
+    // K-major operands are read as one 128-byte segment per row per k-block: 128 (+ batch) rows that lie K*4 bytes apart.
+    // DRAM then serves 128-byte requests scattered over as many pages, at ~2 TB/s (ncu: 29 % of peak) with every loader
+    // warp waiting on its loads. TC_PF_BLOCKS k-blocks ahead of the loads, one thread per row asks L2 for the next
+    // 512 contiguous bytes of its row (4 k-blocks) in ONE request, so that DRAM sees long bursts.
+    constexpr int PF_SPAN = 4;                     // k-blocks per prefetch request (4 x 128 B)
+    auto burst_prefetch = [&](int kb) {
+      if (!(p.tune & 2048) || (kb % PF_SPAN) != 0) return;
+      const int k = (kb + TC_PF_BLOCKS) * BKT;
+      if (k >= p.K) return;
+      const uint32_t bytes = (uint32_t)(((p.K - k < PF_SPAN * BKT) ? (p.K - k) : PF_SPAN * BKT) * 4);
+      if (A_KMAJOR && tid < TC_BM) {
+        if (m0 + tid < p.M) l2_prefetch_bulk(row_ptr(RA, m0 + tid) + k, bytes);
+      } else if (B_KMAJOR && tid >= TC_BM && tid < TC_BM + b_lines) {
+        l2_prefetch_bulk(row_ptr(RB, n0 + tid - TC_BM) + k, bytes);
+      }
+    };
+    if (p.tune & 2048) {                           // the rows' first TC_PF_BLOCKS k-blocks, before the first loads
+      for (int kb = -TC_PF_BLOCKS; kb < 0; kb += PF_SPAN) burst_prefetch(kb - (kb % PF_SPAN));
+    }
 
     for (int kb0 = 0; kb0 < nkb; kb0 += DEPTH) {
 #pragma unroll
@@ -466,6 +504,7 @@ __global__ void __launch_bounds__(LW * 32 + 32, OCC) tc_grouped_gemm_kernel(cons
           store_block(ra[d], rb[d]);
           if (kb == 0 && warp == 0) TC_STAMP(3);
           if (kb + DEPTH < nkb) load_block(kb + DEPTH, ra[d], rb[d]);
+          burst_prefetch(kb);
           if (kb == kb_prefetch) adam_tile_prefetch();
         }
       }
@@ -755,6 +794,20 @@ static inline cudaError_t launch_tc_gemm(TcParams p, int G, cudaStream_t stream)
     p.n_stages = 1;
     return launch_tc_gemm_nb<A_KMAJOR, B_KMAJOR, EPI, 4, 2>(p, G, stream);
   }
+  }
+  if constexpr (EPI != EPI_ADAM && B_KMAJOR) {
+    if (nks <= TC_MAX_ACCUM && (p.tune & 1024)) {
+      // short-K forward / data gradient (the 128 x 256 layer of the 2DMG discriminator, the generator trunks): a tile is
+      // 4-8 k-blocks of MMAs between ~3 us of start-up and ~4 us of epilogue, so one CTA per SM leaves the tensor core idle
+      // most of the time. One accumulation region suffices (<= 43 accumulations): batch tiles of <= 128 lines, one 64 KB
+      // stage and 256 TMEM columns -> two CTAs per SM, one's start-up / epilogue under the other's main loop.
+      const int tiles = (p.N + 127) / 128;
+      p.bn = ((p.N + tiles - 1) / tiles + 15) / 16 * 16;
+      p.n_main = 1;
+      p.tmem_cols = tc_pow2_cols(2 * tc_region_stride(p.bn));
+      p.n_stages = 1;
+      return launch_tc_gemm_nb<A_KMAJOR, B_KMAJOR, EPI, 4, 2>(p, G, stream);
+    }
   }
   p.bn = tc_pick_bn(p.N, p.K);
   p.n_stages = tc_pick_stages(p.bn);

@@ -41,8 +41,24 @@ template <int N>
 __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 
 // MAXCH: 16-column chunks of the N tile the epilogue keeps in registers (7: bn <= 112, 8: bn <= 128)
-template <bool A_KMAJOR, bool B_KMAJOR, int EPI, int MAXCH>
-__global__ void __launch_bounds__(TCP_THREADS, 1) tc_persistent_gemm_kernel(const TcParams p, const int G) {
+// LW: loader warps. 8: the layout above (TCP_VARIANT). 16: 24 warps in six warpgroups -- loaders 0..15, the MMA warp 16
+// (17..19 only fill its warpgroup), epilogue 20..23 -- 768 threads start with 80 registers each; the MMA warpgroup gives
+// up all but 32, the epilogue warpgroup takes 128 (it holds a 32 x 112 accumulator slice), the loaders keep 80 (two
+// k-blocks = 32 registers of loads in flight). Used for the FORWARD product: 16 loader warps were what made the one-tile
+// forward kernel fast (tc_gemm.cuh), and a tile there pays ~2.8 us of start-up, ~2.8 us of epilogue and 2.4 - 4.4 us of
+// CTA turn-around per 20 - 35 us (in-kernel timeline + launch arithmetic, profiles/fwd_sweep_r2.md).
+template <int LW>
+struct TcpLayout {
+  static constexpr int MMA_WARP = LW;
+  static constexpr int EPI_WARP0 = (LW == 16) ? 20 : TCP_EPI_WARP0;
+  static constexpr int THREADS = (LW == 16) ? 768 : TCP_THREADS;
+  static constexpr int DEPTH = (LW == 16) ? 2 : TCP_DEPTH;
+};
+template <bool A_KMAJOR, bool B_KMAJOR, int EPI, int MAXCH, int LW = 8>
+__global__ void __launch_bounds__(TcpLayout<LW>::THREADS, 1) tc_persistent_gemm_kernel(const TcParams p, const int G) {
+  constexpr int MMAW = TcpLayout<LW>::MMA_WARP;
+  constexpr int EPIW0 = TcpLayout<LW>::EPI_WARP0;
+  constexpr int NPA = 32 / LW;        // A patches per loader warp (a 128-line tile has 32 patches of 4 lines / 4 k-rows)
   extern __shared__ __align__(1024) char tc_smem[];
   __shared__ __align__(8) unsigned long long bar_full[TC_MAX_STAGES];
   __shared__ __align__(8) unsigned long long bar_empty[TC_MAX_STAGES];
@@ -53,7 +69,7 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_persistent_gemm_kernel(cons
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int bn = p.bn;
   const int nst = p.n_stages;
-  constexpr int NB = 4;
+  constexpr int NB = 32 / LW;         // B patches per loader warp (bn <= 128)
 
   const uint32_t a_bytes = TC_BM * TC_BK * 4;
   const int bn_pad = (bn + 31) & ~31;
@@ -83,25 +99,25 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_persistent_gemm_kernel(cons
 
   if (tid == 0) {
     for (int i = 0; i < nst; ++i) {
-      mbar_init(smem_u32(&bar_full[i]), TC_LOADER_THREADS);
+      mbar_init(smem_u32(&bar_full[i]), LW * 32);
       mbar_init(smem_u32(&bar_empty[i]), 1);
     }
     mbar_init(smem_u32(&bar_acc_full), 1);
     mbar_init(smem_u32(&bar_acc_empty), 32 * TCP_EPI_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == TC_MMA_WARP) tmem_alloc(smem_u32(&tmem_slot), TC_TMEM_COLS);
+  if (warp == MMAW) tmem_alloc(smem_u32(&tmem_slot), TC_TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = tmem_slot;
 
-  if (warp < TC_MMA_WARP) {
-    if (TCP_VARIANT == 2) setmaxnreg_inc<160>();
+  if (warp < MMAW) {
+    if (LW == 8 && TCP_VARIANT == 2) setmaxnreg_inc<160>();
     // ===== loaders: one flat stream of k-blocks over all tiles of this CTA =====
     const int npb = bn_pad >> 2;
-    constexpr int DEPTH = TCP_DEPTH;
-    float4 ra[DEPTH][4], rb[DEPTH][NB];
+    constexpr int DEPTH = TcpLayout<LW>::DEPTH;
+    float4 ra[DEPTH][NPA], rb[DEPTH][NB];
     const int total = my_tiles * nkb;
     // Per-tile addressing state of the load stream, rebuilt only when the stream enters a new tile (the compiler
     // hoists this by itself in the one-tile-per-CTA kernel; here the tile changes inside the loop):
@@ -109,9 +125,9 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_persistent_gemm_kernel(cons
     //   MN-major operand: column offset t_u per patch (-1 outside); a k-block resolves ONE row pointer (all patches
     //                     of a thread share k = k0 + 4*(warp%8) + lane/8) and adds the offsets
     Rows RA = {}, RB = {};
-    const float* pa[4];
+    const float* pa[NPA];
     const float* pb[NB];
-    int ta[4], tb[NB];
+    int ta[NPA], tb[NB];
     const int kq = 4 * (lane & 7);                 // K-major: k offset inside a k-block
     const int kr = 4 * (warp & 7) + (lane >> 3);   // MN-major: k row inside a k-block
     auto setup_tile = [&](int i) {
@@ -120,8 +136,8 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_persistent_gemm_kernel(cons
       RA = resolve(p.A, g);
       RB = resolve(p.B, g);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int pp = warp + 8 * u;
+      for (int u = 0; u < NPA; ++u) {
+        const int pp = warp + LW * u;
         if (A_KMAJOR) {
           const int t = m0l + 4 * pp + (lane >> 3);
           pa[u] = (t < p.M) ? row_ptr(RA, t) + kq : nullptr;
@@ -132,7 +148,7 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_persistent_gemm_kernel(cons
       }
 #pragma unroll
       for (int u = 0; u < NB; ++u) {
-        const int pp = warp + 8 * u;
+        const int pp = warp + LW * u;
         if (B_KMAJOR) {
           const int t = n0l + 4 * pp + (lane >> 3);
           pb[u] = (pp < npb && t < p.N) ? row_ptr(RB, t) + kq : nullptr;
@@ -143,7 +159,7 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_persistent_gemm_kernel(cons
       }
     };
     int ld_kb = 0, ld_tile = 0;
-    auto load_block = [&](int j, float4 (&qa)[4], float4 (&qb)[NB]) {
+    auto load_block = [&](int j, float4 (&qa)[NPA], float4 (&qb)[NB]) {
       (void)j;                      // loads are issued in increasing j: counters instead of a division per k-block
       const int kb = ld_kb;
       if (kb == 0) setup_tile(ld_tile);
@@ -153,12 +169,12 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_persistent_gemm_kernel(cons
       if (A_KMAJOR) {
         const bool kok = k0 + kq < p.K;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) qa[u] = (kok && pa[u]) ? __ldg(reinterpret_cast<const float4*>(pa[u] + k0)) : zero;
+        for (int u = 0; u < NPA; ++u) qa[u] = (kok && pa[u]) ? __ldg(reinterpret_cast<const float4*>(pa[u] + k0)) : zero;
       } else {
         const int k = k0 + kr;
         const float* rp = (k < p.K) ? row_ptr(RA, k) : nullptr;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) qa[u] = (rp && ta[u] >= 0) ? __ldg(reinterpret_cast<const float4*>(rp + ta[u])) : zero;
+        for (int u = 0; u < NPA; ++u) qa[u] = (rp && ta[u] >= 0) ? __ldg(reinterpret_cast<const float4*>(rp + ta[u])) : zero;
       }
       if (B_KMAJOR) {
         const bool kok = k0 + kq < p.K;
@@ -183,17 +199,17 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_persistent_gemm_kernel(cons
       const int lines = (p.N - n0s < bn) ? (p.N - n0s) : bn;
       npb_st = (lines + 3) >> 2;
     };
-    auto store_block = [&](const float4 (&qa)[4], const float4 (&qb)[NB]) {
+    auto store_block = [&](const float4 (&qa)[NPA], const float4 (&qb)[NB]) {
       if (!st_first) mbar_wait(smem_u32(&bar_empty[st_s]), st_par);
       char* a_hi = smem + (size_t)st_s * stage_bytes;
       char* a_lo = a_hi + a_bytes;
       char* b_hi = a_hi + 2 * a_bytes;
       char* b_lo = b_hi + b_bytes;
 #pragma unroll
-      for (int u = 0; u < 4; ++u) tc_split_store(a_hi, a_lo, tc_patch_offset<A_KMAJOR>(warp + 8 * u, lane), qa[u]);
+      for (int u = 0; u < NPA; ++u) tc_split_store(a_hi, a_lo, tc_patch_offset<A_KMAJOR>(warp + LW * u, lane), qa[u]);
 #pragma unroll
       for (int u = 0; u < NB; ++u) {
-        const int pp = warp + 8 * u;
+        const int pp = warp + LW * u;
         if (pp < npb_st) tc_split_store(b_hi, b_lo, tc_patch_offset<B_KMAJOR>(pp, lane), qb[u]);
       }
       fence_proxy_async_smem();
@@ -218,10 +234,11 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_persistent_gemm_kernel(cons
         }
       }
     }
-  } else if (warp < TCP_EPI_WARP0) {
-    // ===== MMA issuer: one thread of warp 8 (variant 2: warps 9..11 only fill its warpgroup) =====
-    if (TCP_VARIANT == 2) setmaxnreg_dec<40>();
-    if (warp == TC_MMA_WARP) {
+  } else if (warp < EPIW0) {
+    // ===== MMA issuer: one thread of warp MMAW (the rest of its warpgroup, if any, only gives its registers away) =====
+    if (LW == 16) setmaxnreg_dec<32>();
+    else if (TCP_VARIANT == 2) setmaxnreg_dec<40>();
+    if (warp == MMAW) {
       const uint32_t idesc = umma_idesc_tf32(!A_KMAJOR, !B_KMAJOR, bn);
       const uint32_t a_lbo = A_KMAJOR ? 16u : 4096u, a_sbo = A_KMAJOR ? 1024u : 512u;
       const uint32_t b_lbo = B_KMAJOR ? 16u : 4096u, b_sbo = B_KMAJOR ? 1024u : 512u;
@@ -266,7 +283,8 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_persistent_gemm_kernel(cons
     }
   } else {
     // ===== epilogue warps, one per TMEM lane quarter =====
-    if (TCP_VARIANT == 2) setmaxnreg_inc<152>();
+    if (LW == 16) setmaxnreg_inc<128>();
+    else if (TCP_VARIANT == 2) setmaxnreg_inc<152>();
     const int q = warp & 3;   // the TMEM lane quarter a warp may read is fixed by its index
     const int nch = bn >> 4;
     const int n_used = nks < n_main ? nks : n_main;
@@ -339,7 +357,7 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_persistent_gemm_kernel(cons
 
   tc_fence_before();
   __syncthreads();
-  if (warp == TC_MMA_WARP) tmem_dealloc(tmem_d, TC_TMEM_COLS);
+  if (warp == MMAW) tmem_dealloc(tmem_d, TC_TMEM_COLS);
 }
 
 static inline int tc_num_sms() {
@@ -354,11 +372,26 @@ static inline int tc_num_sms() {
 }
 
 // true: launched (or failed with *err set); false: not applicable (the caller uses tc_grouped_gemm_kernel)
+template <bool A_KMAJOR, bool B_KMAJOR, int EPI, int MAXCH, int LW>
+static inline void launch_tc_persistent_inst(const TcParams& p, int G, int grid, size_t smem, cudaStream_t stream, cudaError_t* err) {
+  static unsigned long long attr = 0;
+  if (first_use_on_device(attr)) {
+    *err = cudaFuncSetAttribute(tc_persistent_gemm_kernel<A_KMAJOR, B_KMAJOR, EPI, MAXCH, LW>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BUDGET);
+    if (*err != cudaSuccess) return;
+  }
+  tc_persistent_gemm_kernel<A_KMAJOR, B_KMAJOR, EPI, MAXCH, LW><<<grid, TcpLayout<LW>::THREADS, smem, stream>>>(p, G);
+  count_launch();
+  *err = cudaGetLastError();
+}
+
 template <bool A_KMAJOR, bool B_KMAJOR, int EPI>
 static inline bool launch_tc_persistent(TcParams p, int G, cudaStream_t stream, cudaError_t* err) {
-  // measured (profiles/linear_bench.py): the data-gradient product gains 10-20 % from the persistent kernel, the
-  // forward product loses (its loaders are bound by their own instruction stream, which is longer here)
+  // measured (profiles/linear_bench.py): the data-gradient product gains 10-20 % from the persistent kernel with 8 loader
+  // warps; the forward product loses with 8 (its loaders are bound by their own instruction stream) and runs the
+  // 16-loader-warp layout (tune bit 16)
   if (!(tc_tune() & (A_KMAJOR ? 16 : 8))) return false;
+  if ((tc_tune() & 1024) && (p.K + 7) / 8 <= TC_MAX_ACCUM) return false;   // short K: the two-CTAs-per-SM variant (tc_gemm.cuh)
   p.bn = tc_pick_bn(p.N, p.K);
   if (p.bn > 128 || p.K < 4 * TC_BK) return false;
   p.n_stages = tc_pick_stages(p.bn);
@@ -369,25 +402,10 @@ static inline bool launch_tc_persistent(TcParams p, int G, cudaStream_t stream, 
   const long long tiles = (long long)G * ((p.M + TC_BM - 1) / TC_BM) * ((p.N + p.bn - 1) / p.bn);
   const int sms = tc_num_sms();
   const int grid = (int)(tiles < sms ? tiles : sms);
-  if (p.bn <= 112) {
-    static unsigned long long attr7 = 0;
-    if (first_use_on_device(attr7)) {
-      *err = cudaFuncSetAttribute(tc_persistent_gemm_kernel<A_KMAJOR, B_KMAJOR, EPI, 7>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BUDGET);
-      if (*err != cudaSuccess) return true;
-    }
-    tc_persistent_gemm_kernel<A_KMAJOR, B_KMAJOR, EPI, 7><<<grid, TCP_THREADS, smem, stream>>>(p, G);
-  } else {
-    static unsigned long long attr8 = 0;
-    if (first_use_on_device(attr8)) {
-      *err = cudaFuncSetAttribute(tc_persistent_gemm_kernel<A_KMAJOR, B_KMAJOR, EPI, 8>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BUDGET);
-      if (*err != cudaSuccess) return true;
-    }
-    tc_persistent_gemm_kernel<A_KMAJOR, B_KMAJOR, EPI, 8><<<grid, TCP_THREADS, smem, stream>>>(p, G);
-  }
-  count_launch();
-  *err = cudaGetLastError();
+  *err = cudaSuccess;
+  constexpr int LWX = A_KMAJOR ? 16 : 8;
+  if (p.bn <= 112) launch_tc_persistent_inst<A_KMAJOR, B_KMAJOR, EPI, 7, LWX>(p, G, grid, smem, stream, err);
+  else launch_tc_persistent_inst<A_KMAJOR, B_KMAJOR, EPI, 8, LWX>(p, G, grid, smem, stream, err);
   return true;
 }
 
