@@ -431,8 +431,17 @@ def run_sub_records(h, args, wanted):
                                      total_clients=1024)
             extra["ms_per_step_without_cloud_exchange"] = ms_nc / SUB_STEPS
             extra["cloud_exchange_ms"] = (ms - ms_nc) / SUB_STEPS
+        # ... and the same rounds replayed from a CUDA graph (the cloud all-reduce captured with them): no launch gaps
+        try:
+            ms_g, _, _ = measure_md(h, "cglgan", dataset, C, per, SUB_STEPS, SUB_WARMUP + 2, total_clients=1024, graph=True)
+            extra["ms_per_step_cuda_graph"] = ms_g / SUB_STEPS
+            extra["value_cuda_graph"] = 1024 * SUB_STEPS / (ms_g / 1e3)
+        except Exception as e:
+            extra["cuda_graph_error"] = f"{type(e).__name__}: {e}"[:200]
+            h.free()
         rec = sub_record(h, "strong", f"CGLGAN {dataset.upper()} round, 1024 clients / {1024 // per} servers IN TOTAL dealt over "
-                         f"{W} GPU(s), batch 100, cloud all-reduce every round", 1024, ms, SUB_STEPS, launches, table, dataset,
+                         f"{W} GPU(s), batch 100, cloud all-reduce every round; value = eager rounds (per-kernel events), "
+                         f"value_cuda_graph = MDStyleSim.round_graph", 1024, ms, SUB_STEPS, launches, table, dataset,
                          "strong", extra)
         if "kernel_ms_sum_per_step" in rec:
             # ... and the host side: time of the round not covered by engine kernels (launch gaps, ATen weight math)

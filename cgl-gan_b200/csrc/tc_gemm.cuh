@@ -202,6 +202,17 @@ __host__ __device__ inline uint32_t umma_idesc_tf32(bool a_mn_major, bool b_mn_m
 //       patch p = 4 k x 32 t: k group p%8, t group p/8;  lane -> (k = 4*(p%8) + lane/8, t = 32*(p/8) + 4*(lane%8))
 // BKT = K extent of a staged k-block: 32, or 16 for MN-major operands only (KG = BKT / 4 groups of 4 k-rows per 32 lines;
 // the K-major layout is tied to 32: one 128-byte swizzle row)
+// operand loads: read-only path (default) or, with -DTC_LD_STREAM, streaming loads that do not allocate in L1 (an operand
+// element is read once per CTA and the CTA leaves ~30 KB of L1)
+__device__ __forceinline__ float4 tc_ldg4(const float* p) {
+#ifdef TC_LD_STREAM
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::128B.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+#else
+  return __ldg(reinterpret_cast<const float4*>(p));
+#endif
+}
 template <bool KMAJOR, int BKT = 32>
 __device__ __forceinline__ float4 tc_patch_load(const Rows& R, int p, int lane, int t0, int dimT, int k0, int dimK) {
   static_assert(BKT == 32 || (!KMAJOR && BKT == 16), "unsupported k-block");
@@ -210,11 +221,11 @@ __device__ __forceinline__ float4 tc_patch_load(const Rows& R, int p, int lane, 
   if (KMAJOR) {
     const int t = t0 + 4 * p + (lane >> 3);
     const int k = k0 + 4 * (lane & 7);
-    if (t < dimT && k < dimK) v = __ldg(reinterpret_cast<const float4*>(row_ptr(R, t) + k));
+    if (t < dimT && k < dimK) v = tc_ldg4(row_ptr(R, t) + k);
   } else {
     const int k = k0 + 4 * (p % KG) + (lane >> 3);
     const int t = t0 + 32 * (p / KG) + 4 * (lane & 7);
-    if (k < dimK && t < dimT) v = __ldg(reinterpret_cast<const float4*>(row_ptr(R, k) + t));
+    if (k < dimK && t < dimT) v = tc_ldg4(row_ptr(R, k) + t);
   }
   return v;
 }

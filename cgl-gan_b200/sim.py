@@ -192,9 +192,12 @@ class MDStyleSim:
         networks) a round is ~50 launches of 10-300 us and the host's launch rate, not the GPU, sets the pace.
         The first call runs an eager round (it also sizes every workspace), the second captures, all later calls copy
         the inputs into the captured buffers and replay. Fixed control flow only: cloud_epoch in {0, 1}, E == 0, one
-        process; z_d / z_g must be given either always or never (never: torch.randn inside the graph)."""
+        (any number of ranks); z_d / z_g must be given either always or never (never: torch.randn inside the graph)."""
         k = self.k
-        assert k.E == 0 and k.cloud_epoch in (0, 1) and self.comm is None and not self.profile, "round_graph: unsupported knobs"
+        assert k.E == 0 and k.cloud_epoch in (0, 1) and not self.profile, "round_graph: unsupported knobs"
+        assert self.algo != "capgan" or not k.cloud_epoch, "round_graph: capgan's cloud period is decided on the host"
+        # (with a communicator the cloud all-reduce is captured too: ncclAllReduce on the capturing stream; every rank
+        #  captures and replays the same sequence)
         st = getattr(self, "_graph_state", None)
         if st is None:
             self._graph_state = {"graph": None}

@@ -134,6 +134,33 @@ def check_flgan(rank, local, world, dev, comm):
     return e_d, e_g
 
 
+def check_graph_rounds(rank, local, world, dev, comm):
+    """MDStyleSim.round_graph over a communicator (the cloud all-reduce is captured with the round) == eager rounds."""
+    from cgl_gan_b200 import models
+    from cgl_gan_b200.sim import Knobs, MDStyleSim
+    shape, d, B = (2,), 2, 100
+    W, S = 4, 2                                  # per rank
+    torch.manual_seed(70 + rank)
+    k = Knobs(num_workers=W, num_servers=S, batch_size=B, segema=0.25, iid=1, img_shape=shape)
+    sizes = [300 + 17 * i for i in range(W)]
+    kw = dict(part_sizes=sizes, device=dev, comm=comm, server_offset=rank * S, total_data_len=sum(sizes) * world)
+    a, b = MDStyleSim("cglgan", k, **kw), MDStyleSim("cglgan", k, **kw)
+    g_mods = [a.G.make_module() for _ in range(S)]
+    d_mods = [models.Discriminator(shape) for _ in range(W)]
+    a.load(g_mods, d_mods)
+    b.load(g_mods, d_mods)
+    gen = torch.Generator().manual_seed(90 + rank)
+    for r in range(5):
+        real = torch.tanh(torch.randn(W, B, d, generator=gen)).to(dev)
+        z_d, z_g = torch.randn(S, B, 100, generator=gen).to(dev), torch.randn(S, B, 100, generator=gen).to(dev)
+        la = a.round(real, None, z_d, z_g)
+        lb = b.round_graph(real, None, z_d, z_g)
+        assert torch.equal(la, lb), ("graph round differs", r)
+    torch.cuda.synchronize()
+    assert torch.equal(a.bank.params, b.bank.params) and torch.equal(a.G.trunk.params, b.G.trunk.params)
+    return True
+
+
 def main():
     rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(local)
@@ -144,8 +171,9 @@ def main():
     md = check_mdgan(rank, local, world, dev, comm)
     fe = check_fegan(rank, local, world, dev, comm)
     fl = check_flgan(rank, local, world, dev, comm)
+    gr = check_graph_rounds(rank, local, world, dev, comm)
     if rank == 0:
-        print(f"NCCL_ALGOS ok world={world} mdgan={md} fegan={fe} flgan={fl}", flush=True)
+        print(f"NCCL_ALGOS ok world={world} mdgan={md} fegan={fe} flgan={fl} graph={gr}", flush=True)
     comm.close()
     dist.barrier()
     dist.destroy_process_group()
