@@ -80,6 +80,19 @@ lib.cgl_fl_step_workspace_bytes.argtypes = [C.POINTER(MlpDesc), C.POINTER(MlpDes
 lib.cgl_fl_step_workspace_bytes.restype = _sz
 lib.cgl_fl_step.argtypes = [C.POINTER(MlpDesc), C.POINTER(MlpDesc), _i32, _p, _p, _p, _i64, _p, _p, _i64, _p, _p, _p, _i64, _p,
                             _p, _p, _p, _p, _p, _i32, C.POINTER(TrainCfg), C.POINTER(TrainCfg), _p, _p, _p, _sz, _p]
+lib.cgl_im2col3x3.argtypes = [_i64, _i32, _i32, _i32, _i32, _p, _p, _p]
+lib.cgl_col2im3x3.argtypes = [_i64, _i32, _i32, _i32, _i32, _p, _p, _p]
+lib.cgl_upsample2x.argtypes = [_i64, _i32, _i32, _i32, _p, _p, _p]
+lib.cgl_upsample2x_bwd.argtypes = [_i64, _i32, _i32, _i32, _p, _p, _p]
+lib.cgl_channel_scale.argtypes = [_i64, _i32, _i32, _p, _p, _p]
+lib.cgl_nchw_to_nhwc.argtypes = [_i64, _i32, _i32, _p, _p, _p]
+lib.cgl_nhwc_to_nchw.argtypes = [_i64, _i32, _i32, _p, _p, _p]
+lib.cgl_bn_forward.argtypes = [_i32, _i32, _i32, _p, _p, _p, _i64, _p, _i64, _i64, _p, _i64, _i64, _i64, _p, _p, _f32, _f32,
+                               _i32, _i32, _f32, _p]
+lib.cgl_bn_backward.argtypes = [_i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _i64, _p, _i64, _i64, _p, _f32, _f32, _f32, _f32, _p]
+lib.cgl_act_backward.argtypes = [_i64, _p, _p, _p, _i32, _f32, _p]
+lib.cgl_bn_backward_seg.argtypes = [_i32, _i32, _i32, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _p, _i64, _i64, _p,
+                                    _f32, _f32, _f32, _f32, _p]
 lib.cgl_profile_enable.argtypes = [_i32]
 lib.cgl_profile_tag_name.argtypes = [_i32]
 lib.cgl_profile_tag_name.restype = C.c_char_p
@@ -99,7 +112,9 @@ lib.cgl_linear_bwd_data.argtypes = [_i32, _i32, _i32, _i32, _p, _i64, _p, _i64, 
 lib.cgl_linear_wgrad.argtypes = [_i32, _i32, _i32, _i32, _p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _p]
 
 for _name in ("cgl_arch_describe", "cgl_mlp_layout_of", "cgl_d_step", "cgl_g_loss", "cgl_dxg_reduce",
-              "cgl_adam_rows", "cgl_mix_csr", "cgl_wsum", "cgl_bcast_mix", "cgl_wsum_div", "cgl_fl_step", "cgl_comm_unique_id",
+              "cgl_adam_rows", "cgl_mix_csr", "cgl_wsum", "cgl_bcast_mix", "cgl_wsum_div", "cgl_fl_step", "cgl_im2col3x3",
+              "cgl_col2im3x3", "cgl_upsample2x", "cgl_upsample2x_bwd", "cgl_channel_scale", "cgl_nchw_to_nhwc", "cgl_nhwc_to_nchw",
+              "cgl_bn_forward", "cgl_bn_backward", "cgl_act_backward", "cgl_bn_backward_seg", "cgl_comm_unique_id",
               "cgl_comm_init", "cgl_comm_destroy", "cgl_allreduce_sum", "cgl_mix_allreduce",
               "cgl_linear_fwd", "cgl_linear_bwd_data", "cgl_linear_wgrad", "cgl_set_gemm_mode", "cgl_mlp_forward", "cgl_mlp_backward", "cgl_profile_enable",
               "cgl_profile_summary", "cgl_debug_set_timeline", "cgl_linear_wgrad_adam", "cgl_gather_rows", "cgl_hist2d",

@@ -12,7 +12,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(HERE, "build")
 LIB = os.path.join(LIBDIR, "libcgl_b200.so")
-SOURCES = ["arch.cu", "dstep.cu", "gstep.cu", "mix.cu", "comm.cu", "data.cu", "k1.cu", "fl.cu"]
+SOURCES = ["arch.cu", "dstep.cu", "gstep.cu", "mix.cu", "comm.cu", "data.cu", "fl.cu", "conv.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC"]
 

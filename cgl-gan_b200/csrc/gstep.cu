@@ -484,3 +484,158 @@ extern "C" int cgl_mlp_backward(const cgl_mlp_desc* arch, int G, float* params, 
   }
   return CGL_OK;
 }
+
+// ---- building blocks (the convolutional networks of conv.cu compose them; csrc/conv.cu, cgl-gan_b200/conv.py) ---------
+// BatchNorm over the rows of [G][rows][F] with its affine parameters in packed rows: BatchNorm1d over a batch, or
+// BatchNorm2d when the rows are the pixels of NHWC images (statistics over N*H*W per channel).
+extern "C" int cgl_bn_forward(int G, int rows, int F, const float* u, float* h, const float* params, int64_t ldp,
+                              const int32_t* ids, int64_t gamma_off, int64_t beta_off, float* bn_stats, int64_t ld_stats,
+                              int64_t mean_off, int64_t var_off, float* save_mean, float* save_invstd, float eps,
+                              float momentum, int train, int act, float slope, cgl_stream_t stream) {
+  if (G == 0) return CGL_OK;
+  CGL_REQUIRE(G > 0 && G <= 65535 && rows > 0 && F > 0, "bad shape G=%d rows=%d F=%d", G, rows, F);
+  CGL_REQUIRE(u && h && params && (train || bn_stats), "NULL tensor pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  BnFwdParams b = {};
+  b.rows = rows; b.F = F;
+  b.u = u; b.u_gstride = (long long)rows * F;
+  b.h = h; b.h_gstride = (long long)rows * F;
+  b.params = params; b.ldp = ldp; b.ids = ids; b.gamma_off = gamma_off; b.beta_off = beta_off;
+  b.stats = bn_stats; b.ld_stats = ld_stats; b.mean_off = mean_off; b.var_off = var_off;
+  b.save_mean = save_mean; b.save_invstd = save_invstd;
+  b.eps = eps; b.momentum = momentum; b.train = train; b.act = act; b.slope = slope;
+  dim3 grid((F + 127) / 128, G);
+  ProfScope prof(CGL_PROF_BN_FWD, 8.0 * G * rows * (double)F, 0.0, st);
+  if (bn_smem_ok(rows, F, b.u, b.u_gstride, nullptr, 0, 1)) {
+    static unsigned long long attr = 0;
+    if (first_use_on_device(attr))
+      CGL_CHECK_CUDA(cudaFuncSetAttribute(bn_fwd_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    bn_fwd_smem_kernel<<<grid, 128, (size_t)rows * 512, st>>>(b);
+  } else {
+    bn_fwd_kernel<<<grid, 128, 0, st>>>(b);
+  }
+  CGL_CHECK_LAUNCH();
+  return CGL_OK;
+}
+
+// dz: gradient wrt the BatchNorm OUTPUT, overwritten with the gradient wrt its input; gamma / beta take their Adam step
+// (step[row] must already count this update).
+extern "C" int cgl_bn_backward(int G, int rows, int F, float* dz, const float* u, const float* save_mean,
+                               const float* save_invstd, float* params, float* adam_m, float* adam_v, int64_t ldp,
+                               const int32_t* ids, int64_t gamma_off, int64_t beta_off, const int32_t* step, float lr,
+                               float beta1, float beta2, float eps, cgl_stream_t stream) {
+  if (G == 0) return CGL_OK;
+  CGL_REQUIRE(G > 0 && G <= 65535 && rows > 0 && F > 0, "bad shape G=%d rows=%d F=%d", G, rows, F);
+  CGL_REQUIRE(dz && u && save_mean && save_invstd && params && adam_m && adam_v && step, "NULL tensor pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  BnBwdParams b = {};
+  b.rows = rows; b.F = F;
+  b.dz = dz; b.dz_gstride = (long long)rows * F;
+  b.u = u; b.u_gstride = (long long)rows * F;
+  b.save_mean = save_mean; b.save_invstd = save_invstd;
+  b.params = params; b.adam_m = adam_m; b.adam_v = adam_v; b.ldp = ldp; b.ids = ids;
+  b.gamma_off = gamma_off; b.beta_off = beta_off;
+  b.step = step; b.lr = lr; b.b1 = beta1; b.b2 = beta2; b.eps = eps; b.scal = nullptr;
+  dim3 grid((F + 127) / 128, G);
+  ProfScope prof(CGL_PROF_BN_BWD, 12.0 * G * rows * (double)F, 0.0, st);
+  if (bn_smem_ok(rows, F, b.dz, b.dz_gstride, b.u, b.u_gstride, 2)) {
+    static unsigned long long attr = 0;
+    if (first_use_on_device(attr))
+      CGL_CHECK_CUDA(cudaFuncSetAttribute(bn_bwd_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    bn_bwd_smem_kernel<<<grid, 128, (size_t)rows * 1024, st>>>(b);
+  } else {
+    bn_bwd_kernel<<<grid, 128, 0, st>>>(b);
+  }
+  CGL_CHECK_LAUNCH();
+  return CGL_OK;
+}
+
+// dz = dy * act'(y), y the saved activation OUTPUT
+extern "C" int cgl_act_backward(int64_t n, const float* dy, const float* y, float* dz, int act, float slope,
+                                cgl_stream_t stream) {
+  if (n == 0) return CGL_OK;
+  CGL_REQUIRE(n > 0 && dy && y && dz, "bad arguments");
+  CGL_REQUIRE(aligned16(dy) && aligned16(y) && aligned16(dz), "cgl_act_backward needs 16-byte aligned tensors");
+  const long long nthreads = (n + 3) / 4;
+  act_bwd_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n, dy, y, dz, act, slope);
+  CGL_CHECK_LAUNCH();
+  return CGL_OK;
+}
+
+// BatchNorm backward over TWO row segments that were normalised separately (two forward calls through the same layer:
+// net_d(real) and net_d(fake) each use their own batch statistics, but their gradients meet in ONE optimizer step):
+// dz [G][rows0 + rows1][F], segment 1 follows segment 0; d gamma / d beta are summed over both, Adam is applied once.
+namespace cgl {
+__global__ void __launch_bounds__(128) bn_bwd_seg_kernel(int rows0, int rows1, int F, float* dz, const float* __restrict__ u,
+                                                        const float* __restrict__ mean0, const float* __restrict__ invstd0,
+                                                        const float* __restrict__ mean1, const float* __restrict__ invstd1,
+                                                        float* params, float* adam_m, float* adam_v, long long ldp, const int* ids,
+                                                        long long gamma_off, long long beta_off, const int* step, float lr, float b1,
+                                                        float b2, float eps) {
+  const int g = blockIdx.y;
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= F) return;
+  const int rowid = ids ? ids[g] : g;
+  const long long gs = (long long)(rows0 + rows1) * F;
+  float* d = dz + (long long)g * gs + f;
+  const float* x = u + (long long)g * gs + f;
+  const long long go = (long long)rowid * ldp + gamma_off + f, bo = (long long)rowid * ldp + beta_off + f;
+  const float gamma = params[go];
+  float dgamma = 0.f, dbeta = 0.f;
+  for (int seg = 0; seg < 2; ++seg) {
+    const int n = seg ? rows1 : rows0;
+    if (n == 0) continue;
+    const float mean = (seg ? mean1 : mean0)[(long long)g * F + f];
+    const float invstd = (seg ? invstd1 : invstd0)[(long long)g * F + f];
+    float* ds = d + (long long)(seg ? rows0 : 0) * F;
+    const float* xs = x + (long long)(seg ? rows0 : 0) * F;
+    float sb0 = 0.f, sb1 = 0.f, sg0 = 0.f, sg1 = 0.f;
+    int r = 0;
+    for (; r + 1 < n; r += 2) {
+      const float d0 = ds[(long long)r * F], d1 = ds[(long long)(r + 1) * F];
+      sb0 += d0; sb1 += d1;
+      sg0 = fmaf(d0, xs[(long long)r * F] - mean, sg0);
+      sg1 = fmaf(d1, xs[(long long)(r + 1) * F] - mean, sg1);
+    }
+    for (; r < n; ++r) {
+      const float d0 = ds[(long long)r * F];
+      sb0 += d0;
+      sg0 = fmaf(d0, xs[(long long)r * F] - mean, sg0);
+    }
+    const float sb = sb0 + sb1, dotp = sg0 + sg1;
+    dbeta += sb;
+    dgamma += dotp * invstd;
+    const float k = dotp * invstd * invstd / (float)n, mb = sb / (float)n, a = invstd * gamma;
+    for (r = 0; r < n; ++r) ds[(long long)r * F] = (ds[(long long)r * F] - mb - (xs[(long long)r * F] - mean) * k) * a;
+  }
+  const AdamScalars s = make_adam_scalars(step[rowid], lr, b1, b2, eps);
+  {
+    float w = gamma, mm = adam_m[go], vv = adam_v[go];
+    adam_update(w, mm, vv, dgamma, s);
+    params[go] = w; adam_m[go] = mm; adam_v[go] = vv;
+  }
+  {
+    float w = params[bo], mm = adam_m[bo], vv = adam_v[bo];
+    adam_update(w, mm, vv, dbeta, s);
+    params[bo] = w; adam_m[bo] = mm; adam_v[bo] = vv;
+  }
+}
+}  // namespace cgl
+
+extern "C" int cgl_bn_backward_seg(int G, int rows0, int rows1, int F, float* dz, const float* u, const float* mean0,
+                                   const float* invstd0, const float* mean1, const float* invstd1, float* params,
+                                   float* adam_m, float* adam_v, int64_t ldp, const int32_t* ids, int64_t gamma_off,
+                                   int64_t beta_off, const int32_t* step, float lr, float beta1, float beta2, float eps,
+                                   cgl_stream_t stream) {
+  if (G == 0) return CGL_OK;
+  CGL_REQUIRE(G > 0 && G <= 65535 && rows0 >= 0 && rows1 >= 0 && rows0 + rows1 > 0 && F > 0, "bad shape");
+  CGL_REQUIRE(dz && u && mean0 && invstd0 && (rows1 == 0 || (mean1 && invstd1)) && params && adam_m && adam_v && step,
+              "NULL tensor pointer");
+  dim3 grid((F + 127) / 128, G);
+  ProfScope prof(CGL_PROF_BN_BWD, 12.0 * G * (double)(rows0 + rows1) * F, 0.0, (cudaStream_t)stream);
+  cgl::bn_bwd_seg_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(rows0, rows1, F, dz, u, mean0, invstd0, mean1, invstd1, params,
+                                                                adam_m, adam_v, ldp, ids, gamma_off, beta_off, step, lr, beta1,
+                                                                beta2, eps);
+  CGL_CHECK_LAUNCH();
+  return CGL_OK;
+}

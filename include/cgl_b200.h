@@ -302,6 +302,42 @@ int cgl_linear_wgrad_adam(int G, int rows, int in, int out, const float* dy, int
                           const int32_t* step, const int32_t* ids, int64_t w_off, int64_t b_off, float lr, float beta1,
                           float beta2, float eps, void* adam_scratch, cgl_stream_t stream);
 
+/* ---- convolutional LSGAN networks (model/lsgan.py:3-27 Generator, :73-99 Discriminator) -------------
+ * The reference ships these classes without a call site; the engine runs them as implicit GEMMs over the grouped Linear
+ * products above. Activations are [N images][H*W pixels][C channels] (NHWC; N = groups x batch), a 3x3 convolution
+ * (padding 1, stride 1 or 2) of a group is   cgl_im2col3x3 -> cgl_linear_fwd(rows = B*OH*OW, in = C*9, out = Cout)   with
+ * Conv2d.weight [Cout][Cin][3][3] read as the Linear weight [out][in] (im2col columns ordered (ci, kh, kw)), its backward
+ * cgl_linear_wgrad_adam + cgl_linear_bwd_data -> cgl_col2im3x3. The host-side composition is cgl-gan_b200/conv.py.
+ *   cgl_im2col3x3      col[n][oh][ow][ci*9+kh*3+kw] = x[n][oh*s-1+kh][ow*s-1+kw][ci]  (0 outside)
+ *   cgl_col2im3x3      its transpose: dx[n][ih][iw][ci] = sum of the taps that read that pixel (gathered, fixed order)
+ *   cgl_upsample2x     nn.Upsample(scale_factor=2) (nearest), H x W -> 2H x 2W;  _bwd: the sum of each 2 x 2 block
+ *   cgl_channel_scale  x[n][pix][c] *= mask[n][c]: Dropout2d(0.25) with the mask injected (model/lsgan.py:79), also its backward
+ *   cgl_nchw_to_nhwc / cgl_nhwc_to_nchw   out.view(B, 128, 8, 8) after l1 (:22-23) and out.view(B, -1) before adv_layer (:96-97)
+ *   cgl_bn_forward / cgl_bn_backward   BatchNorm over the rows of [G][rows][F] (BatchNorm2d(C, 0.8) when rows are NHWC
+ *                      pixels), parameters / running statistics in packed rows; backward takes gamma / beta's Adam step
+ *   cgl_act_backward   dz = dy * act'(y)                                                                              */
+int cgl_im2col3x3(int64_t N, int H, int W, int C, int stride, const float* x, float* col, cgl_stream_t stream);
+int cgl_col2im3x3(int64_t N, int H, int W, int C, int stride, const float* dcol, float* dx, cgl_stream_t stream);
+int cgl_upsample2x(int64_t N, int H, int W, int C, const float* x, float* y, cgl_stream_t stream);
+int cgl_upsample2x_bwd(int64_t N, int H, int W, int C, const float* dy, float* dx, cgl_stream_t stream);
+int cgl_channel_scale(int64_t N, int HW, int C, const float* mask, float* x, cgl_stream_t stream);
+int cgl_nchw_to_nhwc(int64_t N, int C, int HW, const float* x, float* y, cgl_stream_t stream);
+int cgl_nhwc_to_nchw(int64_t N, int C, int HW, const float* x, float* y, cgl_stream_t stream);
+int cgl_bn_forward(int G, int rows, int F, const float* u, float* h, const float* params, int64_t ldp, const int32_t* ids,
+                   int64_t gamma_off, int64_t beta_off, float* bn_stats, int64_t ld_stats, int64_t mean_off, int64_t var_off,
+                   float* save_mean, float* save_invstd, float eps, float momentum, int train, int act, float slope,
+                   cgl_stream_t stream);
+int cgl_bn_backward(int G, int rows, int F, float* dz, const float* u, const float* save_mean, const float* save_invstd,
+                    float* params, float* adam_m, float* adam_v, int64_t ldp, const int32_t* ids, int64_t gamma_off,
+                    int64_t beta_off, const int32_t* step, float lr, float beta1, float beta2, float eps, cgl_stream_t stream);
+int cgl_act_backward(int64_t n, const float* dy, const float* y, float* dz, int act, float slope, cgl_stream_t stream);
+/* BatchNorm backward over two row segments normalised by two separate forward calls (net_d(real), net_d(fake): each pass
+ * has its own batch statistics, their gradients meet in one optimizer step): dz / u are [G][rows0 + rows1][F]. */
+int cgl_bn_backward_seg(int G, int rows0, int rows1, int F, float* dz, const float* u, const float* mean0, const float* invstd0,
+                        const float* mean1, const float* invstd1, float* params, float* adam_m, float* adam_v, int64_t ldp,
+                        const int32_t* ids, int64_t gamma_off, int64_t beta_off, const int32_t* step, float lr, float beta1,
+                        float beta2, float eps, cgl_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -146,3 +146,74 @@ def weights_init(m):
     elif classname.find('Linear') != -1:
         nn.init.normal_(m.weight.data, 0.0, 0.02)
         nn.init.constant_(m.bias.data, 0)
+
+
+class ConvGenerator(nn.Module):
+    """model/lsgan.py:3-27 (the ims argument is unused there too)."""
+
+    def __init__(self, ims=None):
+        super().__init__()
+        self.init_size = 32 // 4
+        self.l1 = nn.Sequential(nn.Linear(100, 128 * self.init_size ** 2))
+        self.conv_blocks = nn.Sequential(
+            nn.Upsample(scale_factor=2),
+            nn.Conv2d(128, 128, 3, stride=1, padding=1),
+            nn.BatchNorm2d(128, 0.8),
+            nn.LeakyReLU(0.2, inplace=True),
+            nn.Upsample(scale_factor=2),
+            nn.Conv2d(128, 64, 3, stride=1, padding=1),
+            nn.BatchNorm2d(64, 0.8),
+            nn.LeakyReLU(0.2, inplace=True),
+            nn.Conv2d(64, 1, 3, stride=1, padding=1),
+            nn.Tanh(),
+        )
+
+    def forward(self, z):
+        out = self.l1(z)
+        out = out.view(out.shape[0], 128, self.init_size, self.init_size)
+        return self.conv_blocks(out)
+
+
+class ConvDiscriminator(nn.Module):
+    """model/lsgan.py:73-99. forward(img, masks): masks = None runs the modules as the reference does (nn.Dropout2d draws
+    its own noise); a list of four [B, C] tensors replaces the noise of the four Dropout2d layers (F.dropout2d multiplies by
+    a [B, C, 1, 1] tensor of bernoulli(1 - p) / (1 - p)), so that the engine and the oracle drop the same channels."""
+
+    def __init__(self, ims=None):
+        super().__init__()
+
+        def discriminator_block(in_filters, out_filters, bn=True):
+            block = [nn.Conv2d(in_filters, out_filters, 3, 2, 1), nn.LeakyReLU(0.2, inplace=True), nn.Dropout2d(0.25)]
+            if bn:
+                block.append(nn.BatchNorm2d(out_filters, 0.8))
+            return block
+
+        self.model = nn.Sequential(
+            *discriminator_block(1, 16, bn=False),
+            *discriminator_block(16, 32),
+            *discriminator_block(32, 64),
+            *discriminator_block(64, 128),
+        )
+        ds_size = 32 // 2 ** 4
+        self.adv_layer = nn.Linear(128 * ds_size ** 2, 1)
+
+    def forward(self, img, masks=None):
+        if masks is None:
+            out = self.model(img)
+        else:
+            out, k = img, 0
+            for m in self.model:
+                if isinstance(m, nn.Dropout2d):
+                    out = out * masks[k][:, :, None, None]
+                    k += 1
+                else:
+                    out = m(out)
+        out = out.view(out.shape[0], -1)
+        return self.adv_layer(out)
+
+
+def draw_dropout2d_masks(B, p=0.25):
+    """The noise of the discriminator's four Dropout2d layers, drawn from torch's global RNG exactly as one training-mode
+    forward draws it (feature dropout: bernoulli(1 - p) of shape [B, C, 1, 1], divided by 1 - p)."""
+    import torch.nn.functional as F
+    return [F.dropout2d(torch.ones(B, C, 1, 1), p, training=True).reshape(B, C) for C in (16, 32, 64, 128)]

@@ -267,11 +267,39 @@ def golden_sharing():
     return out, arrays
 
 
+def golden_conv_lsgan():
+    """model/lsgan.py Generator / Discriminator (no call site in the scripts): initial weights by hash, one training-mode
+    forward of each (BatchNorm2d batch statistics; Dropout2d noise from the seeded global RNG), one eval-mode forward."""
+    torch.set_num_threads(1)
+    ref = load("model/lsgan.py", "ref_lsgan")
+    torch.manual_seed(20211212)
+    net_g, net_d = ref.Generator(None), ref.Discriminator(None)
+    out = {"g_sha": sha(flat(net_g)), "d_sha": sha(flat(net_d))}
+    g = torch.Generator().manual_seed(41)
+    z = torch.randn(4, 100, generator=g)
+    img = net_g(z)
+    torch.manual_seed(5)
+    val = net_d(img.detach())
+    out["img_train"] = summary(img)
+    out["val_train"] = [float(v) for v in val.reshape(-1).tolist()]
+    out["g_stats"] = summary(torch.cat([b.reshape(-1) for n, b in net_g.named_buffers() if "running" in n]))
+    out["d_stats"] = summary(torch.cat([b.reshape(-1) for n, b in net_d.named_buffers() if "running" in n]))
+    net_g.eval(); net_d.eval()
+    with torch.no_grad():
+        img_e = net_g(z)
+        val_e = net_d(img_e)
+    out["img_eval"] = summary(img_e)
+    out["val_eval"] = [float(v) for v in val_e.reshape(-1).tolist()]
+    torch.set_num_threads(os.cpu_count())
+    return {"conv_lsgan": out}
+
+
 if __name__ == "__main__":
     steps, arrays = golden_server_updates()
     s2, a2 = golden_sharing()
     steps.update(s2)
     arrays.update(a2)
+    steps.update(golden_conv_lsgan())
     json.dump(steps, open(os.path.join(OUT, "steps2.json"), "w"), indent=1)
     np.savez_compressed(os.path.join(OUT, "steps2_arrays.npz"), **arrays)
     print("wrote steps2.json, steps2_arrays.npz:", sorted(steps))

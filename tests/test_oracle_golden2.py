@@ -174,3 +174,38 @@ def test_mdgan_swap_matches_reference_statements():
         rd = random.Random(int(rank) + 100)
         for expect in rounds:
             assert st.mdgan_swap(list(range(10)), rd) == expect
+
+
+def test_conv_lsgan_classes_match_reference():
+    """oracle.models.ConvGenerator / ConvDiscriminator == model/lsgan.py's classes: same initial weights for a seed, the same
+    training-mode forward (BatchNorm2d batch statistics, Dropout2d noise from the seeded global RNG) and eval-mode forward."""
+    gold = STEPS["conv_lsgan"]
+    torch.manual_seed(20211212)
+    net_g, net_d = om.ConvGenerator(None), om.ConvDiscriminator(None)
+    assert _sha(_flat(net_g)) == gold["g_sha"] and _sha(_flat(net_d)) == gold["d_sha"]
+    g = torch.Generator().manual_seed(41)
+    z = torch.randn(4, 100, generator=g)
+    img = net_g(z)
+    torch.manual_seed(5)
+    val = net_d(img.detach())
+    _check_summary(img, gold["img_train"])
+    assert np.allclose(val.reshape(-1).tolist(), gold["val_train"], atol=1e-6)
+    _check_summary(torch.cat([b.reshape(-1) for n, b in net_g.named_buffers() if "running" in n]), gold["g_stats"])
+    _check_summary(torch.cat([b.reshape(-1) for n, b in net_d.named_buffers() if "running" in n]), gold["d_stats"])
+    # the injected-mask path is the same forward: the masks one training-mode forward draws, fed back in
+    torch.manual_seed(5)
+    masks = om.draw_dropout2d_masks(4)
+    net_d2 = om.ConvDiscriminator(None)
+    net_d2.load_state_dict({k: v for k, v in net_d.state_dict().items()})
+    torch.manual_seed(5)
+    a = net_d2(img.detach())
+    net_d3 = om.ConvDiscriminator(None)
+    net_d3.load_state_dict({k: v for k, v in net_d.state_dict().items()})
+    b = net_d3(img.detach(), masks)
+    assert torch.equal(a, b)
+    net_g.eval(); net_d.eval()
+    with torch.no_grad():
+        img_e = net_g(z)
+        val_e = net_d(img_e)
+    _check_summary(img_e, gold["img_eval"])
+    assert np.allclose(val_e.reshape(-1).tolist(), gold["val_eval"], atol=1e-6)
