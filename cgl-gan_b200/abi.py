@@ -59,6 +59,8 @@ lib.cgl_g_loss_workspace_bytes.argtypes = [C.POINTER(MlpDesc), _i32, _i32]
 lib.cgl_g_loss_workspace_bytes.restype = _sz
 lib.cgl_d_step.argtypes = [C.POINTER(MlpDesc), _i32, _p, _p, _p, _i64, _p, _p, _p, _p, _p, _p, _i32,
                            C.POINTER(TrainCfg), _p, _p, _sz, _p]
+lib.cgl_client_step.argtypes = [C.POINTER(MlpDesc), _i32, _p, _p, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _i32,
+                                C.POINTER(TrainCfg), _p, _p, _p, _p, _sz, _p]
 lib.cgl_g_loss.argtypes = [C.POINTER(MlpDesc), _i32, _p, _i64, _p, _p, _p, _i32, _i32, _p, _p, _p, _sz, _p]
 lib.cgl_dxg_reduce.argtypes = [_i32, _p, _p, _p, _p, _i64, _p, _p]
 lib.cgl_adam_rows.argtypes = [_i32, _i64, _i64, _p, _p, _p, _p, _p, _f32, _f32, _f32, _f32, _p]
@@ -104,6 +106,9 @@ lib.cgl_gather_rows.argtypes = [_i64, _i32, _p, _i64, _p, _p, _p]
 lib.cgl_hist2d.argtypes = [_i64, _p, _i64, _p, _p]
 lib.cgl_kl_score_2d.argtypes = [_i64, _p, _i64, _p, _p, _p, _p]
 lib.cgl_set_gemm_mode.argtypes = [_i32]
+lib.cgl_set_fused_client_step.argtypes = [_i32]
+lib.cgl_set_fused_client_step.restype = C.c_int
+lib.cgl_get_fused_client_step.restype = C.c_int
 lib.cgl_debug_set_timeline.argtypes = [_p]
 lib.cgl_get_gemm_mode.restype = C.c_int
 lib.cgl_linear_fwd.argtypes = [_i32, _i32, _i32, _i32, _p, _i64, _p, _i64, _p, _i64, _i64, _i32, _f32, _p, _i64, _p]
@@ -111,7 +116,7 @@ lib.cgl_linear_bwd_data.argtypes = [_i32, _i32, _i32, _i32, _p, _i64, _p, _i64, 
                                     _p, _i64, _p]
 lib.cgl_linear_wgrad.argtypes = [_i32, _i32, _i32, _i32, _p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _p]
 
-for _name in ("cgl_arch_describe", "cgl_mlp_layout_of", "cgl_d_step", "cgl_g_loss", "cgl_dxg_reduce",
+for _name in ("cgl_arch_describe", "cgl_mlp_layout_of", "cgl_d_step", "cgl_g_loss", "cgl_client_step", "cgl_dxg_reduce",
               "cgl_adam_rows", "cgl_mix_csr", "cgl_wsum", "cgl_bcast_mix", "cgl_wsum_div", "cgl_fl_step", "cgl_im2col3x3",
               "cgl_col2im3x3", "cgl_upsample2x", "cgl_upsample2x_bwd", "cgl_channel_scale", "cgl_nchw_to_nhwc", "cgl_nhwc_to_nchw",
               "cgl_bn_forward", "cgl_bn_backward", "cgl_act_backward", "cgl_bn_backward_seg", "cgl_comm_unique_id",
@@ -131,7 +136,7 @@ def version():
     return lib.cgl_version().decode()
 
 
-PROF_NUM_TAGS = 13
+PROF_NUM_TAGS = 14
 
 
 def profile_enable(on=True):

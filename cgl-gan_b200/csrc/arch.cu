@@ -45,7 +45,7 @@ extern "C" long long cgl_launch_count(void) { return g_launches; }
 static const char* kProfNames[CGL_PROF_NUM_TAGS] = {
     "linear_fwd[tcgen05]", "linear_bwd_data[tcgen05]", "linear_wgrad+adam[tcgen05]", "linear_wgrad[tcgen05]",
     "linear_fwd[ffma]", "linear_bwd_data[ffma]", "linear_wgrad+adam[ffma]", "linear_wgrad[ffma]",
-    "head_loss", "batchnorm_fwd", "batchnorm_bwd", "mix/aggregate", "elementwise"};
+    "head_loss", "batchnorm_fwd", "batchnorm_bwd", "mix/aggregate", "elementwise", "client_step_fused[ffma]"};
 
 extern "C" int cgl_profile_enable(int on) {
   for (auto& r : g_prof) { g_prof_pool.push_back(r.a); g_prof_pool.push_back(r.b); }

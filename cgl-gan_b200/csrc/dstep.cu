@@ -1,6 +1,7 @@
 // dstep.cu -- the per-client discriminator step and generator-loss evaluation (K1/K2).
 // Reference: Worker.train, CGLGAN/2DMG/main.py:344-375; capgan.py:316-349; MDGAN/MNIST/mdgan.py:266-297.
 #include "linear.cuh"
+#include "client_fused.cuh"
 #include <stdlib.h>
 
 namespace cgl {
@@ -486,6 +487,57 @@ static int launch_head(const cgl_mlp_desc* a, const cgl_mlp_layout& lay, int G, 
   return CGL_OK;
 }
 
+// ---- K1: the fused, shared-memory-resident client step (client_fused.cuh) ----------------------------------------
+// cgl_set_fused_client_step(0 / 1) (or CGL_K1=0 / 1 in the environment) switches it; the FFMA-only / tcgen05-only GEMM
+// modes of cgl_set_gemm_mode keep the layered kernels, so the parity tests that run in two modes compare the two.
+static int initial_k1() {
+  const char* e = getenv("CGL_K1");
+  return (e && (e[0] == '0' || e[0] == '1') && e[1] == 0) ? e[0] - '0' : K1_DEFAULT_ON;
+}
+static int g_k1_on = initial_k1();
+static bool k1_enabled() { return g_k1_on != 0 && g_gemm_mode == GEMM_AUTO; }
+static bool k1_eligible(const cgl_mlp_desc* a, const cgl_mlp_layout& lay, int loss_kind, int B, const void* params,
+                        const void* am, const void* av, long long ldp) {
+  if (!k1_enabled()) return false;
+  if (a->n_layers != 3 || a->dims[0] < 1 || a->dims[0] > K1_MAXD || a->dims[1] != K1_H1 || a->dims[2] != K1_H2 ||
+      a->dims[3] != 1)
+    return false;
+  if (a->act[0] != CGL_ACT_LRELU || a->act[1] != CGL_ACT_LRELU) return false;
+  if (loss_kind != CGL_LOSS_BCE && loss_kind != CGL_LOSS_MSE) return false;
+  if (B < 1 || 2 * B > K1_MAXROWS) return false;
+  if (ldp % 4 != 0 || lay.w_off[1] % 4 != 0 || !aligned16(params) || (am && !aligned16(am)) || (av && !aligned16(av)))
+    return false;
+  return true;
+}
+static int launch_k1(const cgl_mlp_desc* a, const cgl_mlp_layout& lay, int G, float* params, float* am, float* av,
+                     long long ldp, int* step, const int* ids, const float* real, const int* n_real, const float* fake,
+                     const int* fake_idx, const float* xg, const int* xg_idx, int B, int loss_kind, float d_scale,
+                     const cgl_train_cfg* cfg, float* out_dloss, float* out_gloss, float* out_dxg, int do_d, int do_g,
+                     cudaStream_t st) {
+  K1Params k = {};
+  k.d = a->dims[0]; k.B = B;
+  k.params = params; k.adam_m = am; k.adam_v = av; k.ldp = ldp; k.ids = ids; k.step = step;
+  for (int l = 0; l < 3; ++l) { k.w_off[l] = lay.w_off[l]; k.b_off[l] = lay.b_off[l]; }
+  k.real = real; k.n_real = n_real; k.fake = fake; k.fake_idx = fake_idx; k.xg = xg; k.xg_idx = xg_idx;
+  k.out_dloss = out_dloss; k.out_gloss = out_gloss; k.out_dxg = out_dxg;
+  k.loss_kind = loss_kind; k.last_act = a->act[2]; k.slope = a->lrelu_slope; k.d_scale = d_scale;
+  if (cfg) { k.lr = cfg->lr; k.b1 = cfg->beta1; k.b2 = cfg->beta2; k.eps = cfg->eps; }
+  k.do_d = do_d; k.do_g = do_g;
+  static unsigned long long attr_set = 0;
+  if (first_use_on_device(attr_set))
+    CGL_CHECK_CUDA(cudaFuncSetAttribute(client_step_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)K1_SMEM_BYTES));
+  // algorithmic work: MACs = B (8 M - 2 M1) for both parts, 24 B per parameter + the batches
+  const double M1 = (double)a->dims[0] * K1_H1, M = M1 + (double)K1_H1 * K1_H2 + K1_H2;
+  const double macs = (do_d ? 2.0 * B * (3.0 * M - M1) : 0.0) + (do_g ? 2.0 * B * M : 0.0);
+  const double bytes = (do_d ? 24.0 * (double)lay.n_params + 8.0 * B * a->dims[0] : 4.0 * (double)lay.n_params) +
+                       (do_g ? 8.0 * B * a->dims[0] : 0.0);
+  ProfScope prof(CGL_PROF_CLIENT_FUSED, G * bytes, 2.0 * G * macs, st);
+  client_step_fused_kernel<<<G, K1_THREADS, K1_SMEM_BYTES, st>>>(k);
+  CGL_CHECK_LAUNCH();
+  return CGL_OK;
+}
+
 }  // namespace cgl
 
 using namespace cgl;
@@ -520,6 +572,9 @@ extern "C" int cgl_d_step(const cgl_mlp_desc* arch, int G, float* params, float*
     return CGL_EWORKSPACE;
   }
   cudaStream_t st = (cudaStream_t)stream;
+  if (k1_eligible(arch, lay, cfg->loss_kind, B, params, adam_m, adam_v, ldp))
+    return launch_k1(arch, lay, G, params, adam_m, adam_v, ldp, step, client_ids, real, n_real, fake, fake_idx, nullptr,
+                     nullptr, B, cfg->loss_kind, cfg->d_loss_scale, cfg, out_dloss, nullptr, nullptr, 1, 0, st);
   Workspace w = carve(arch, G, rows, workspace);
   const int L = arch->n_layers;
   const int d = arch->dims[0];
@@ -570,6 +625,9 @@ extern "C" int cgl_g_loss(const cgl_mlp_desc* arch, int G, const float* params, 
     return CGL_EWORKSPACE;
   }
   cudaStream_t st = (cudaStream_t)stream;
+  if (k1_eligible(arch, lay, loss_kind, B, params, nullptr, nullptr, ldp))
+    return launch_k1(arch, lay, G, const_cast<float*>(params), nullptr, nullptr, ldp, nullptr, client_ids, nullptr, nullptr,
+                     nullptr, nullptr, xg, xg_idx, B, loss_kind, 1.f, nullptr, nullptr, out_loss, out_dxg, 0, 1, st);
   Workspace w = carve(arch, G, B, workspace);
   const int L = arch->n_layers;
   const int d = arch->dims[0];
@@ -595,12 +653,47 @@ extern "C" int cgl_g_loss(const cgl_mlp_desc* arch, int G, const float* params, 
   return CGL_OK;
 }
 
+// The whole client step of a round in one call: the D step on (real, fake), then the G loss and dLoss/dXg through the
+// UPDATED discriminator (Worker.train, CGLGAN/2DMG/main.py:344-375 with epoch == 1). One launch per call where the fused
+// shared-memory-resident kernel applies (client_fused.cuh), otherwise cgl_d_step followed by cgl_g_loss.
+extern "C" int cgl_client_step(const cgl_mlp_desc* arch, int G, float* params, float* adam_m, float* adam_v, int64_t ldp,
+                               int32_t* step, const int32_t* client_ids, const float* real, const int32_t* n_real,
+                               const float* fake, const int32_t* fake_idx, const float* xg, const int32_t* xg_idx, int B,
+                               const cgl_train_cfg* cfg, float* out_dloss, float* out_gloss, float* out_dxg,
+                               void* workspace, size_t workspace_bytes, cgl_stream_t stream) {
+  CGL_REQUIRE(cfg != nullptr, "cfg is NULL");
+  int rc = validate_d_arch(arch, cfg->loss_kind);
+  if (rc) return rc;
+  if (G == 0) return CGL_OK;
+  CGL_REQUIRE(G > 0 && G <= 65535, "G=%d out of range (1..65535 groups per call)", G);
+  CGL_REQUIRE(B > 0, "B must be positive");
+  CGL_REQUIRE(params && adam_m && adam_v && step && real && fake && xg && out_dloss && out_gloss, "NULL tensor pointer");
+  cgl_mlp_layout lay;
+  rc = cgl_mlp_layout_of(arch, &lay);
+  if (rc) return rc;
+  CGL_REQUIRE(ldp >= lay.n_params, "ldp=%lld smaller than packed row (%lld)", (long long)ldp, (long long)lay.n_params);
+  if (k1_eligible(arch, lay, cfg->loss_kind, B, params, adam_m, adam_v, ldp))
+    return launch_k1(arch, lay, G, params, adam_m, adam_v, ldp, step, client_ids, real, n_real, fake, fake_idx, xg, xg_idx,
+                     B, cfg->loss_kind, cfg->d_loss_scale, cfg, out_dloss, out_gloss, out_dxg, 1, 1,
+                     (cudaStream_t)stream);
+  rc = cgl_d_step(arch, G, params, adam_m, adam_v, ldp, step, client_ids, real, n_real, fake, fake_idx, B, cfg, out_dloss,
+                  workspace, workspace_bytes, stream);
+  if (rc) return rc;
+  return cgl_g_loss(arch, G, params, ldp, client_ids, xg, xg_idx, B, cfg->loss_kind, out_gloss, out_dxg, workspace,
+                    workspace_bytes, stream);
+}
+
 extern "C" int cgl_set_gemm_mode(int mode) {
   CGL_REQUIRE(mode == GEMM_AUTO || mode == GEMM_FFMA || mode == GEMM_TC, "gemm mode must be 0 (auto), 1 (FFMA) or 2 (tcgen05)");
   g_gemm_mode = mode;
   return CGL_OK;
 }
 extern "C" int cgl_get_gemm_mode(void) { return g_gemm_mode; }
+extern "C" int cgl_set_fused_client_step(int on) {
+  g_k1_on = on ? 1 : 0;
+  return CGL_OK;
+}
+extern "C" int cgl_get_fused_client_step(void) { return g_k1_on; }
 
 // Bring-up only: CTA (0,0,g) of every tcgen05 GEMM launched from this translation unit (cgl_d_step, cgl_g_loss,
 // cgl_linear_*) stamps clock64() at its milestones into buf[g*16 + i] (csrc/tc_gemm.cuh). NULL switches it off.

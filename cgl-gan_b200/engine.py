@@ -111,6 +111,30 @@ class ClientBank:
         self.launches += self.desc.n_layers + (self.desc.n_layers - 1 if need_grad else 0)
         return loss, dxg
 
+    def client_step(self, real, fake, xg, n_real=None, idx=None, client_ids=None, need_grad=True):
+        """d_step(real, fake[idx]) followed by g_loss_raw(xg[idx]) in ONE ABI call (cgl_client_step): one Worker.train
+        call with epoch == 1, CGLGAN/2DMG/main.py:344-375. idx None: client g owns fake[g] / xg[g].
+        For the 2DMG discriminator this is one kernel launch with the client's weights resident in shared memory."""
+        G, B = real.shape[0], self.B
+        real = real.reshape(G, B, self.d).contiguous()
+        fake = fake.reshape(-1, B, self.d).contiguous()
+        xg = xg.reshape(-1, B, self.d).contiguous()
+        assert real.dtype == torch.float32 and fake.dtype == torch.float32 and xg.dtype == torch.float32
+        n_real, idx, client_ids = _i32(n_real, self.device), _i32(idx, self.device), _i32(client_ids, self.device)
+        if idx is None:
+            assert fake.shape[0] >= G and xg.shape[0] >= G
+        d_loss = torch.empty(G, device=self.device)
+        g_loss = torch.empty(G, device=self.device)
+        dxg = torch.empty(G, B, self.d, device=self.device) if need_grad else None
+        nbytes = abi.lib.cgl_d_step_workspace_bytes(C.byref(self.desc), G, B)
+        ws = self._workspace(nbytes)
+        abi.check(abi.lib.cgl_client_step(C.byref(self.desc), G, abi.ptr(self.params), abi.ptr(self.adam_m),
+                                          abi.ptr(self.adam_v), self.ld, abi.ptr(self.step), abi.ptr(client_ids),
+                                          abi.ptr(real), abi.ptr(n_real), abi.ptr(fake), abi.ptr(idx), abi.ptr(xg),
+                                          abi.ptr(idx), B, C.byref(self.cfg), abi.ptr(d_loss), abi.ptr(g_loss),
+                                          abi.ptr(dxg), abi.ptr(ws), ws.numel(), _stream()))
+        return d_loss, g_loss, dxg
+
     def g_loss(self, xg, xg_idx=None, client_ids=None):
         """Graph-attached client losses: the tensor the reference's workers put on servers[id].queen_g
         (CGLGAN/2DMG/main.py:373). Backward delivers sum_g grad[g] * dloss_g/dxg to xg."""

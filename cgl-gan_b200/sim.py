@@ -162,10 +162,13 @@ class MDStyleSim:
         if self.profile:
             ev0 = torch.cuda.Event(enable_timing=True)
             ev0.record()
-        for e in range(real.shape[0]):
+        E = real.shape[0]
+        for e in range(E - 1):
             self.last_d_loss = self.bank.d_step(real[e], Xd, n_real=None if n_real is None else n_real[e],
                                                 fake_idx=idx)
-        loss, dxg = self.bank.g_loss_raw(Xg_flat, xg_idx=idx)
+        # the last D step and the G loss through the updated D: one ABI call (one launch for the 2DMG discriminator)
+        self.last_d_loss, loss, dxg = self.bank.client_step(real[E - 1], Xd, Xg_flat,
+                                                            n_real=None if n_real is None else n_real[E - 1], idx=idx)
         loss = loss.view(S, N)
         if self.profile:
             ev1 = torch.cuda.Event(enable_timing=True)

@@ -132,6 +132,21 @@ int cgl_g_loss(const cgl_mlp_desc* arch, int G, const float* params, int64_t ldp
                int loss_kind, float* out_loss, float* out_dxg, void* workspace,
                size_t workspace_bytes, cgl_stream_t stream);
 
+/* ---- K1: the whole client step of a round in ONE call ---------------------------------------
+ * Replaces one Worker.train call with epoch == 1 and one server: CGLGAN/2DMG/main.py:344-375 (the D loop :357-366,
+ * then the tail :368-373 through the UPDATED D), MDGAN/2DMG/mdgan.py:252-278, ACGAN/2DMG/acgan.py:231-257.
+ * = cgl_d_step followed by cgl_g_loss on the same rows. For the small 2DMG discriminator
+ * (CGLGAN/2DMG/model.py:54-71: d <= 4 -> 128 -> 256 -> 1, BCE or MSE) this is ONE kernel launch with one CTA per
+ * client: the client's weights are read from HBM once, stay in shared memory through forward, loss, backward, the
+ * fused Adam update and the generator-loss pass (csrc/client_fused.cuh); cgl_d_step and cgl_g_loss take the same
+ * kernel for these networks when called on their own. Other discriminators run the layered kernels.
+ * workspace: cgl_d_step_workspace_bytes(arch, G, B) bytes.                                          */
+int cgl_client_step(const cgl_mlp_desc* arch, int G, float* params, float* adam_m, float* adam_v, int64_t ldp,
+                    int32_t* step, const int32_t* client_ids, const float* real, const int32_t* n_real,
+                    const float* fake, const int32_t* fake_idx, const float* xg, const int32_t* xg_idx, int B,
+                    const cgl_train_cfg* cfg, float* out_dloss, float* out_gloss, float* out_dxg,
+                    void* workspace, size_t workspace_bytes, cgl_stream_t stream);
+
 /* out[s] = sum_{j in [srv_ptr[s], srv_ptr[s+1])} weights[clients[j]] * dxg[clients[j]]
  * (weights NULL = 1, clients NULL = identity). Replaces the accumulation of every client's
  * dLoss/dXg into a shared Xg during F_max.backward(): capgan.py:258, MDGAN/MNIST/mdgan.py:203-204. */
@@ -257,7 +272,8 @@ int cgl_mix_allreduce(cgl_comm_t comm, int C_local, int64_t n, const float* w_lo
 #define CGL_PROF_BN_BWD 10
 #define CGL_PROF_MIX 11
 #define CGL_PROF_ELEMENTWISE 12
-#define CGL_PROF_NUM_TAGS 13
+#define CGL_PROF_CLIENT_FUSED 13
+#define CGL_PROF_NUM_TAGS 14
 int cgl_profile_enable(int on);
 const char* cgl_profile_tag_name(int tag);
 int cgl_profile_summary(int tag, double* out_ms, double* out_bytes, double* out_flops, long long* out_launches);
@@ -272,6 +288,10 @@ int cgl_profile_summary(int tag, double* out_ms, double* out_bytes, double* out_
 #define CGL_GEMM_TC 2
 int cgl_set_gemm_mode(int mode);
 int cgl_get_gemm_mode(void);
+/* The fused shared-memory-resident client step (cgl_client_step, csrc/client_fused.cuh) on / off for the networks it
+ * covers; off = the layered kernels. Process-wide; CGL_K1=0|1 in the environment presets it. Not a reference knob. */
+int cgl_set_fused_client_step(int on);
+int cgl_get_fused_client_step(void);
 /* Bring-up only: per-CTA clock64() milestones of the tcgen05 GEMM (csrc/tc_gemm.cuh); NULL switches it off. */
 int cgl_debug_set_timeline(long long* device_buf);
 
