@@ -431,6 +431,20 @@ def run_sub_records(h, args, wanted):
                                      total_clients=1024)
             extra["ms_per_step_without_cloud_exchange"] = ms_nc / SUB_STEPS
             extra["cloud_exchange_ms"] = (ms - ms_nc) / SUB_STEPS
+        if dataset == "2dmg":
+            # K1: the same rounds with the OTHER client-step implementation (the one that is not the default): the fused
+            # shared-memory-resident kernel of csrc/client_fused.cuh (one launch per client step) against the layered kernels
+            was = h.abi.lib.cgl_get_fused_client_step()
+            try:
+                h.abi.check(h.abi.lib.cgl_set_fused_client_step(0 if was else 1))
+                ms_k, launches_k, table_k = measure_md(h, "cglgan", dataset, C, per, SUB_STEPS, SUB_WARMUP, total_clients=1024)
+                key = "layered_client_step" if was else "fused_client_step"
+                extra[key] = {"ms_per_step": ms_k / SUB_STEPS, "value": 1024 * SUB_STEPS / (ms_k / 1e3),
+                              "gpu_launches_per_step": launches_k / SUB_STEPS,
+                              "kernels_ms_per_step": {k: v["ms_per_round"] for k, v in table_k.items()}}
+                extra["client_step_default"] = "fused (csrc/client_fused.cuh)" if was else "layered (grouped GEMM kernels)"
+            finally:
+                h.abi.check(h.abi.lib.cgl_set_fused_client_step(was))
         # ... and the same rounds replayed from a CUDA graph (the cloud all-reduce captured with them): no launch gaps
         try:
             ms_g, _, _ = measure_md(h, "cglgan", dataset, C, per, SUB_STEPS, SUB_WARMUP + 2, total_clients=1024, graph=True)

@@ -1,7 +1,8 @@
 """K1, the fused shared-memory-resident client step (csrc/client_fused.cuh), against the oracle's Worker.train
 (CGLGAN/2DMG/main.py:344-375) and against the layered kernels of the same library on identical inputs.
 Bars: losses 1e-5 / 1e-4, parameters the bars of helpers.assert_params_close; fused vs layered on the same inputs before
-any Adam step: dLoss/dXg within 2e-6 of its scale on EVERY element (both are exact-fp32 FMA chains, other summation order)."""
+any Adam step: dLoss/dXg within 5e-6 of its scale on EVERY element (K1: 3xTF32 products on mma.sync, ~5e-7 relative like the
+tcgen05 kernels; layered FFMA mode: exact-fp32 FMA chains)."""
 import pytest
 import torch
 
@@ -92,11 +93,11 @@ def test_fused_and_layered_kernels_agree(lib):
         finally:
             abi.check(abi.lib.cgl_set_gemm_mode(0))
     a, b = out[0], out[1]
-    assert (a["l0"] - b["l0"]).abs().max() < 1e-6
-    assert (a["dx0"] - b["dx0"]).abs().max() <= 2e-6 * b["dx0"].abs().max()
-    assert (a["d"] - b["d"]).abs().max() < 1e-6
+    assert (a["l0"] - b["l0"]).abs().max() < 2e-6
+    assert (a["dx0"] - b["dx0"]).abs().max() <= 5e-6 * b["dx0"].abs().max()
+    assert (a["d"] - b["d"]).abs().max() < 2e-6
     # Adam's first moment after one step is (1 - beta1) * gradient: a direct, well-conditioned view of every gradient
-    assert (a["m"] - b["m"]).abs().max() <= 2e-6 * b["m"].abs().max()
+    assert (a["m"] - b["m"]).abs().max() <= 5e-6 * b["m"].abs().max()
     assert (a["v"] - b["v"]).abs().max() <= 1e-5 * b["v"].abs().max()
     assert torch.equal(a["step"], b["step"])
     for g in range(G):
