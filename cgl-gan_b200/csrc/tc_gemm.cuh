@@ -61,7 +61,7 @@ constexpr int TC_THREADS = TC_LOADER_THREADS + 32;
 #define TC_LW16_DEPTH 3   // k-blocks of loads in flight per thread of the 16-loader-warp forward kernel
 #endif
 constexpr int TC_MAX_BN = 256;
-constexpr int TC_TUNE_DEFAULT = 1 | 8 | 32 | 64 | 256 | 512 | 1024;
+constexpr int TC_TUNE_DEFAULT = 1 | 8 | 32 | 64 | 256 | 512 | 1024 | 131072;
 constexpr uint32_t TC_WAIT_HINT_NS = 20000u;
 
 // ---- PTX wrappers ----------------------------------------------------------------------------
@@ -262,6 +262,7 @@ __device__ long long* g_tc_timeline = nullptr;
 struct TcParams {
   int M, N, K;
   int bn;         // N tile (multiple of 16, <= 256)
+  int n_per;      // tc_tma.cuh: row pitch of the batch tiles (<= bn)
   int n_stages;   // shared-memory stages (1..TC_MAX_STAGES)
   int n_main;     // hi*hi accumulator regions (see "TMEM plan")
   int tmem_cols;  // TMEM columns to allocate: power of two >= (n_main + 1) * round_up(bn, 32)
@@ -281,7 +282,9 @@ struct TcParams {
              // 1024 = two CTAs per SM for short-K (<= 43 k-steps) forward / data-gradient products,
              // 2048 = 512-byte row prefetches into L2, 4096 / 8192 = bring-up ablations (no global loads / no MMAs),
              // 16384 / 32768 = persistent kernel with the lean 16-warp loader loop (tc_sweep.cuh) for forward / data gradient,
-             // 65536 = CTA pairs also for an odd number of M tiles
+             // 65536 = CTA pairs also for an odd number of M tiles,
+             // 131072 = TMA-fed kernel with the weights in TMEM (tc_tma.cuh) for forward / data gradient (524288: its B operand
+             // through registers instead of TMA, 1048576: its one-thread MMA issue loop; 4096 / 8192: its ablations)
 };
 
 // TMEM plan (512 columns, 1 CTA per SM). The tensor core TRUNCATES when it adds into an fp32
