@@ -132,6 +132,32 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// The issue loop runs on a CONVERGED warp: every lane executes it with identical operands and the instructions themselves run
+// on the lane elect.sync picks. Inside an `if (lane == 0)` region nvcc wraps each tcgen05.mma in a waterfall loop (ELECT /
+// R2UR / UTCHMMA / BRA.U.ANY) and the issuing thread needs ~135 clk per MMA -- more than twice what the tensor core takes
+// for a 128 x 112 x 8 tf32 MMA (56 clk; profiles/umma_rate_probe_r2.log, profiles/tma_ablate_r2.log).
+// One k-step of the 3xTF32 product: corr += lo*hi, corr += hi*lo, main (+)= hi*hi.
+__device__ __forceinline__ void umma_kstep_ss_warp(uint32_t d_corr, uint32_t d_main, uint64_t dah, uint64_t dal, uint64_t dbh,
+                                                   uint64_t dbl, uint32_t idesc, uint32_t acc_corr, uint32_t acc_main) {
+  asm volatile(
+      "{\n\t.reg .pred pc, pm, e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 pc, %7, 0;\n\t"
+      "setp.ne.b32 pm, %8, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], %3, %4, %6, pc;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], %2, %5, %6, 1;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%1], %2, %4, %6, pm;\n\t}"
+      ::"r"(d_corr), "r"(d_main), "l"(dah), "l"(dal), "l"(dbh), "l"(dbl), "r"(idesc), "r"(acc_corr), "r"(acc_main)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_warp(uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+      ::"r"(bar)
+      : "memory");
+}
 // 32 lanes x 16 consecutive fp32 columns: thread i of the warp gets lane (base + i)
 __device__ __forceinline__ void tmem_ld16_async(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
@@ -362,45 +388,47 @@ __global__ void __launch_bounds__(LW * 32 + 32, OCC) tc_grouped_gemm_kernel(cons
   if (warp == 0) TC_STAMP(1);
 
   if (warp == MMAW) {
-    // ===== MMA issuer: one thread =====
-    if (lane == 0) {
+    // ===== MMA issuer: the warp runs the loop converged, the elected lane issues (umma_kstep_ss_warp) =====
+    {
       const uint32_t idesc = umma_idesc_tf32(!A_KMAJOR, !B_KMAJOR, bn);
       // K-major : SWIZZLE_128B, SBO = 1024 (next 8 lines), LBO unused, a k-step of 8 = 32 B inside the span
       // MN-major: SWIZZLE_128B_BASE32B, LBO = 4096 (next 32 lines), SBO = 512 (next 4 k), a k-step of 8 = 1024 B
       const uint32_t a_lbo = A_KMAJOR ? 16u : (uint32_t)(KG * 512), a_sbo = A_KMAJOR ? 1024u : 512u;
       const uint32_t b_lbo = B_KMAJOR ? 16u : (uint32_t)(KG * 512), b_sbo = B_KMAJOR ? 1024u : 512u;
-      const uint32_t a_step = A_KMAJOR ? 32u : 1024u, b_step = B_KMAJOR ? 32u : 1024u;
+      constexpr uint64_t a_dstep = (A_KMAJOR ? 32u : 1024u) >> 4, b_dstep = (B_KMAJOR ? 32u : 1024u) >> 4;   // descriptor units
       const uint32_t a_lay = A_KMAJOR ? UMMA_LAYOUT_SW128 : UMMA_LAYOUT_SW128_BASE32B;
       const uint32_t b_lay = B_KMAJOR ? UMMA_LAYOUT_SW128 : UMMA_LAYOUT_SW128_BASE32B;
-      int ks = 0, s = 0, reg = 0;  // k-step counter, stage, main region of the next k-step
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_d, 0);
+      const uint32_t main_lo = tmem_u + (uint32_t)stride, main_hi = tmem_u + (uint32_t)(n_main * stride);
+      const uint32_t bar_f = smem_u32(&bar_full[0]), bar_e = smem_u32(&bar_empty[0]);
+      const uint32_t smem0 = smem_u32(smem);
+      const bool no_mma = (p.tune & 8192) != 0;   // (bring-up: what the loop costs without the tensor core)
+      uint32_t d_main = main_lo;
+      int ks = 0, s = 0;  // k-step counter, stage
       uint32_t par = 0;
       for (int kb = 0; kb < nkb; ++kb) {
-        mbar_wait(smem_u32(&bar_full[s]), par);
+        mbar_wait(bar_f + 8u * s, par);
         if (kb == 0) TC_STAMP(8);
         tc_fence_after();
-        const uint32_t sa_hi = smem_u32(smem + (size_t)s * stage_bytes);
-        const uint32_t sa_lo = sa_hi + a_bytes, sb_hi = sa_hi + 2 * a_bytes, sb_lo = sb_hi + b_bytes;
+        const uint32_t sa_hi = smem0 + (uint32_t)s * stage_bytes;
+        const uint64_t dah0 = umma_desc(sa_hi, a_lbo, a_sbo, a_lay);
+        const uint64_t dal0 = umma_desc(sa_hi + a_bytes, a_lbo, a_sbo, a_lay);
+        const uint64_t dbh0 = umma_desc(sa_hi + 2 * a_bytes, b_lbo, b_sbo, b_lay);
+        const uint64_t dbl0 = umma_desc(sa_hi + 2 * a_bytes + b_bytes, b_lbo, b_sbo, b_lay);
 #pragma unroll
         for (int j = 0; j < BKT / 8; ++j) {
           if (ks < nks) {
-            const uint64_t dah = umma_desc(sa_hi + j * a_step, a_lbo, a_sbo, a_lay);
-            const uint64_t dal = umma_desc(sa_lo + j * a_step, a_lbo, a_sbo, a_lay);
-            const uint64_t dbh = umma_desc(sb_hi + j * b_step, b_lbo, b_sbo, b_lay);
-            const uint64_t dbl = umma_desc(sb_lo + j * b_step, b_lbo, b_sbo, b_lay);
-            const uint32_t main_col = (uint32_t)((1 + reg) * stride);
-            if (++reg == n_main) reg = 0;
-            if (!(p.tune & 8192)) {   // (bring-up: 8192 = no MMAs, what the loop costs without the tensor core)
-              umma_tf32(tmem_d, dal, dbh, idesc, ks > 0 ? 1u : 0u);
-              umma_tf32(tmem_d, dah, dbl, idesc, 1u);
-              umma_tf32(tmem_d + main_col, dah, dbh, idesc, ks >= n_main ? 1u : 0u);
-            }
+            if (!no_mma)
+              umma_kstep_ss_warp(tmem_u, d_main, dah0 + a_dstep * j, dal0 + a_dstep * j, dbh0 + b_dstep * j, dbl0 + b_dstep * j,
+                                 idesc, ks > 0 ? 1u : 0u, ks >= n_main ? 1u : 0u);
+            d_main = (d_main == main_hi) ? main_lo : d_main + (uint32_t)stride;
             ++ks;
           }
         }
-        umma_commit(smem_u32(&bar_empty[s]));
+        umma_commit_warp(bar_e + 8u * s);
         if (++s == nst) { s = 0; par ^= 1u; }
       }
-      umma_commit(smem_u32(&bar_done));
+      umma_commit_warp(smem_u32(&bar_done));
       TC_STAMP(9);
     }
     __syncwarp();

@@ -33,7 +33,7 @@
 
 #include <type_traits>
 
-#include "tc_gemm.cuh"
+#include "tc_pair.cuh"
 
 namespace cgl {
 
@@ -90,14 +90,6 @@ __device__ __forceinline__ void umma_kstep_ts_warp(uint32_t d_corr, uint32_t d_m
       ::"r"(d_corr), "r"(d_main), "r"(a_hi), "r"(a_lo), "l"(dbh), "l"(dbl), "r"(idesc), "r"(acc_corr), "r"(acc_main)
       : "memory");
 }
-__device__ __forceinline__ void umma_commit_warp(uint32_t bar) {
-  asm volatile(
-      "{\n\t.reg .pred e;\n\t"
-      "elect.sync _|e, 0xffffffff;\n\t"
-      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
-      ::"r"(bar)
-      : "memory");
-}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
@@ -105,6 +97,30 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst_smem, const CUtensorMap
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
       ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+      : "memory");
+}
+
+// the same k-step on a CTA pair (cta_group::2: M = 256, A from the TMEM of both CTAs, each CTA's shared memory holds half of
+// the B lines), and the commit that arrives on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void umma_kstep_ts_warp_pair(uint32_t d_corr, uint32_t d_main, uint32_t a_hi, uint32_t a_lo, uint64_t dbh,
+                                                        uint64_t dbl, uint32_t idesc, uint32_t acc_corr, uint32_t acc_main) {
+  asm volatile(
+      "{\n\t.reg .pred pc, pm, e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 pc, %7, 0;\n\t"
+      "setp.ne.b32 pm, %8, 0;\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::tf32 [%0], [%3], %4, %6, pc;\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::tf32 [%0], [%2], %5, %6, 1;\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::tf32 [%1], [%2], %4, %6, pm;\n\t}"
+      ::"r"(d_corr), "r"(d_main), "r"(a_hi), "r"(a_lo), "l"(dbh), "l"(dbl), "r"(idesc), "r"(acc_corr), "r"(acc_main)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair_warp(uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
+      ::"r"(bar), "h"((uint16_t)3)
       : "memory");
 }
 
@@ -120,7 +136,12 @@ struct RingPos {
 
 // B is K-major (lines = batch rows). EPI: EPI_FWD (A K-major: forward) / EPI_BWD_DATA (A MN-major: data gradient; saved == NULL
 // stores the plain product). LWB = loader warps (multiple of 4).
-template <bool A_KMAJOR, int EPI, int LWB, bool BT>
+// PAIR (needs BT): two CTAs of a cluster (adjacent M tiles of one group) run every MMA together (cta_group::2, issued by the CTA
+// of cluster rank 0): each stages, splits and holds only HALF of the batch lines (n_per / 2 rows, accumulator columns
+// [0, bn/2) and [bn/2, bn)), which takes 49 of the 130 KB per k-block off each CTA's shared-memory pipe -- what bounds the
+// one-CTA kernel (profiles/tma_ablate_r2.log). The peer's MMA warp forwards its full barriers to the leader (one remote
+// arrive each); the commits arrive on the empty barriers of both CTAs. An odd number of M tiles adds a CTA without rows.
+template <bool A_KMAJOR, int EPI, int LWB, bool BT, bool PAIR>
 __global__ void __launch_bounds__((LWB + 10) * 32, 1)
 tc_tma_gemm_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapAt,
                    const __grid_constant__ CUtensorMap tmapB0, const __grid_constant__ CUtensorMap tmapB1) {
@@ -139,14 +160,19 @@ tc_tma_gemm_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapA, 
   __shared__ __align__(8) unsigned long long bar_b_raw[TC_MAX_STAGES];
   __shared__ __align__(8) unsigned long long bar_b_full[TC_MAX_STAGES];
   __shared__ __align__(8) unsigned long long bar_b_empty[TC_MAX_STAGES];
+  __shared__ __align__(8) unsigned long long bar_peer_a[TCT_MAX_AS];     // PAIR, leader: the peer's A stage is full
+  __shared__ __align__(8) unsigned long long bar_peer_b[TC_MAX_STAGES];  // PAIR, leader: the peer's B stage is full
   __shared__ __align__(8) unsigned long long bar_done;
   __shared__ uint32_t tmem_slot;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = blockIdx.z;
-  const int m0 = blockIdx.y * TC_BM;
-  const int n0 = blockIdx.x * p.n_per;  // batch tiles start at multiples of n_per <= bn (BT: never inside two sources)
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  // (a kernel that uses cta_group::2 is only accepted with an even cluster width in x: the pair lies along x)
+  const int m0 = (PAIR ? blockIdx.x : blockIdx.y) * TC_BM;
+  const int n0 = (PAIR ? blockIdx.y : blockIdx.x) * p.n_per;  // batch tiles start at multiples of n_per <= bn (BT: never inside two sources)
   const int bn = p.bn;
+  const int hp = p.n_per >> 1, bh = bn >> 1;   // PAIR: batch rows / accumulator columns per CTA
   const int n_valid = (p.N - n0 < p.n_per) ? (p.N - n0) : p.n_per;   // rows of this tile that are stored
   const int nsb = p.n_stages;          // B stages in shared memory
   const int n_main = p.n_main;
@@ -172,18 +198,24 @@ tc_tma_gemm_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapA, 
     for (int i = 0; i < TCT_MAX_AS; ++i) {
       mbar_init(smem_u32(&bar_a_full[i]), 4);
       mbar_init(smem_u32(&bar_a_empty[i]), 1);
+      mbar_init(smem_u32(&bar_peer_a[i]), 1);
     }
     for (int i = 0; i < TC_MAX_STAGES; ++i) {
       mbar_init(smem_u32(&bar_b_raw[i]), 1);
       mbar_init(smem_u32(&bar_b_full[i]), LT);
       mbar_init(smem_u32(&bar_b_empty[i]), 1);
+      mbar_init(smem_u32(&bar_peer_b[i]), 1);
     }
     mbar_init(smem_u32(&bar_done), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == MMAW) tmem_alloc(smem_u32(&tmem_slot), TC_TMEM_COLS);
+  if (warp == MMAW) {
+    if (PAIR) tmem_alloc_pair(smem_u32(&tmem_slot), TC_TMEM_COLS);
+    else tmem_alloc(smem_u32(&tmem_slot), TC_TMEM_COLS);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();   // barriers initialised and TMEM allocated in both CTAs before anything is signalled
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = tmem_slot;
   // bring-up ablations (CGL_TUNE): 4096 = MMAs only (nothing is fed, the MMA thread never waits: what the tensor pipe
@@ -198,10 +230,11 @@ tc_tma_gemm_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapA, 
       // B source of this tile: rows [n0, n0 + n_per) lie in one source (host-checked)
       const bool src1 = BT && n0 >= p.B.rows0;
       const CUtensorMap* tmapB = src1 ? &tmapB1 : &tmapB0;
-      int b_row = n0, b_grp = 0;
+      int b_row = n0 + (PAIR ? (int)rank * hp : 0), b_grp = 0;
+      const uint32_t b_tx = (uint32_t)(PAIR ? hp : p.n_per) * 128u;   // the box is n_per (PAIR: n_per / 2) rows: always inside its source
       if (BT) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmapB)) : "memory");
-        if (src1) { b_row = n0 - p.B.rows0; b_grp = p.B.idx1 ? p.B.idx1[g] : g; }
+        if (src1) { b_row -= p.B.rows0; b_grp = p.B.idx1 ? p.B.idx1[g] : g; }
         else b_grp = p.B.idx0 ? p.B.idx0[g] : g;
       }
       RingPos r = {0, 0}, rb = {0, 0};
@@ -209,7 +242,7 @@ tc_tma_gemm_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapA, 
         if (BT) {
           if (rb.round > 0) mbar_wait(smem_u32(&bar_b_empty[rb.slot]), (rb.round - 1) & 1u);   // the MMAs that read it are done
           const uint32_t bbar = smem_u32(&bar_b_raw[rb.slot]);
-          mbar_arrive_expect_tx(bbar, (uint32_t)p.n_per * 128u);    // the box is n_per rows: always inside its source
+          mbar_arrive_expect_tx(bbar, b_tx);
           tma_load_3d(smem_u32(smem_b + (size_t)rb.slot * bstage_bytes), tmapB, kb * BKT, b_row, b_grp, bbar);
           rb.next(nsb);
         }
@@ -221,7 +254,9 @@ tc_tma_gemm_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapA, 
         // (profiles/tma_repro.py faults with the operand at the end of its allocation), and behind the last matrix of the
         // last bank row there may be nothing mapped. Rows of the stage the tail box leaves unwritten only reach
         // accumulator rows m >= M (forward) or k-steps that are never issued (data gradient, K % 8 == 0).
-        if (A_KMAJOR) {                      // box (32 k, 128 | M % 128 rows m): 128-byte rows, SWIZZLE_128B
+        if (PAIR && m0 >= p.M) {             // the CTA that completes an odd number of M tiles: no rows, nothing to fetch
+          mbar_arrive(bar);
+        } else if (A_KMAJOR) {               // box (32 k, 128 | M % 128 rows m): 128-byte rows, SWIZZLE_128B
           const bool tail = m0 + TC_BM > p.M;
           mbar_arrive_expect_tx(bar, tail ? (uint32_t)(p.M - m0) * 128u : (uint32_t)TCT_RAW_BYTES);
           tma_load_3d(dst, tail ? &tmapAt : &tmapA, kb * BKT, m0, rowid, bar);
@@ -238,7 +273,7 @@ tc_tma_gemm_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapA, 
     // ===== MMA issuer: the whole warp runs the loop converged, the elected lane issues (see umma_tf32_ts_warp) =====
     // The loop is the critical instruction stream of the kernel (one warp, dependent issue): the first k-block (accumulate
     // flags) and a ragged last one (k-steps beyond K) are peeled off so that the blocks in between are branch-free.
-    if (p.tune & 1048576) {
+    if (!PAIR && (p.tune & 1048576)) {
       // (comparison: the one-thread issue loop this kernel started with -- ~135 clk per MMA)
       if (lane == 0) {
         const uint32_t idesc = umma_idesc_tf32(false, false, bn);
@@ -276,21 +311,48 @@ tc_tma_gemm_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapA, 
         }
         umma_commit(smem_u32(&bar_done));
       }
+    } else if (PAIR && rank != 0) {
+      // ===== forwarder (the peer's MMA warp): this CTA's stages are full -> one cluster-scope arrive each on the leader =====
+      if (lane == 0) {
+        const uint32_t peer_b0 = mapa_shared(smem_u32(&bar_peer_b[0]), 0), peer_a0 = mapa_shared(smem_u32(&bar_peer_a[0]), 0);
+        int sb = 0, sa = 0;
+        uint32_t pb = 0, pa = 0;
+        for (int kb = 0; kb < nkb_feed; ++kb) {
+          // one remote arrive per k-block (a release at cluster scope costs the forwarding thread ~0.5 us): the B stage and
+          // both A stages of the block are full
+          mbar_wait(smem_u32(&bar_b_full[sb]), pb);
+          for (int h = 0; h < 2; ++h) {
+            if (kb * 4 + h * 2 < nks) {
+              mbar_wait(smem_u32(&bar_a_full[sa]), pa);
+              if (++sa == nas) { sa = 0; pa ^= 1u; }
+            }
+          }
+          tc_fence_after();
+          tc_fence_before();
+          mbar_arrive_cluster(peer_b0 + 8u * (uint32_t)sb);
+          if (++sb == nsb) { sb = 0; pb ^= 1u; }
+          (void)peer_a0;
+        }
+      }
     } else {
-      const uint32_t idesc = umma_idesc_tf32(false, false, bn);
+      const uint32_t idesc = PAIR ? umma_idesc_tf32_pair(false, false, bn) : umma_idesc_tf32(false, false, bn);
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_d, 0);
       const uint32_t tmem_a0 = tmem_u + a_col0;
       const uint32_t main_lo = tmem_u + (uint32_t)stride, main_hi = tmem_u + (uint32_t)(n_main * stride);   // first / last main region
       const uint32_t sb0 = smem_u32(smem_b);
       const uint32_t bar_bf = smem_u32(&bar_b_full[0]), bar_be = smem_u32(&bar_b_empty[0]);
       const uint32_t bar_af = smem_u32(&bar_a_full[0]), bar_ae = smem_u32(&bar_a_empty[0]);
+      const uint32_t bar_pa = smem_u32(&bar_peer_a[0]), bar_pb = smem_u32(&bar_peer_b[0]);
       uint32_t d_main = main_lo;           // main region of the next k-step
       int sb = 0, sa = 0;
       uint32_t pb = 0, pa = 0;             // parities of the current rounds
       // one 32-wide k-block: FIRST = accumulate flags of the first k-steps, KS = k-steps that carry data (1..4)
       auto block = [&](auto first_c, int nks_here, int ks0) {
         constexpr bool FIRST = decltype(first_c)::value;
-        if (!mma_only) mbar_wait(bar_bf + 8u * sb, pb);
+        if (!mma_only) {
+          mbar_wait(bar_bf + 8u * sb, pb);
+          if (PAIR) mbar_wait_cluster(bar_pb + 8u * sb, pb);
+        }
         tc_fence_after();
         const uint32_t sb_hi = sb0 + (uint32_t)sb * bstage_bytes;
         const uint64_t dbh0 = umma_desc(sb_hi, 16u, 1024u, UMMA_LAYOUT_SW128);
@@ -298,25 +360,35 @@ tc_tma_gemm_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapA, 
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           if (h * 2 < nks_here) {
-            if (!mma_only) mbar_wait(bar_af + 8u * sa, pa);
+            if (!mma_only) {
+              mbar_wait(bar_af + 8u * sa, pa);
+            }
             tc_fence_after();
             const uint32_t ta = tmem_a0 + (uint32_t)(sa * 32);
 #pragma unroll
             for (int jj = 0; jj < 2; ++jj) {
               const int j = h * 2 + jj;
               if (j < nks_here) {
-                if (!no_mma)
-                  umma_kstep_ts_warp(tmem_u, d_main, ta + (uint32_t)(jj * 8), ta + (uint32_t)(jj * 8 + 16),
-                                     dbh0 + (uint64_t)(2 * j), dbl0 + (uint64_t)(2 * j), idesc,
-                                     FIRST ? (ks0 + j > 0 ? 1u : 0u) : 1u, FIRST ? (ks0 + j >= n_main ? 1u : 0u) : 1u);
+                if (!no_mma) {
+                  if (PAIR)
+                    umma_kstep_ts_warp_pair(tmem_u, d_main, ta + (uint32_t)(jj * 8), ta + (uint32_t)(jj * 8 + 16),
+                                            dbh0 + (uint64_t)(2 * j), dbl0 + (uint64_t)(2 * j), idesc,
+                                            FIRST ? (ks0 + j > 0 ? 1u : 0u) : 1u, FIRST ? (ks0 + j >= n_main ? 1u : 0u) : 1u);
+                  else
+                    umma_kstep_ts_warp(tmem_u, d_main, ta + (uint32_t)(jj * 8), ta + (uint32_t)(jj * 8 + 16),
+                                       dbh0 + (uint64_t)(2 * j), dbl0 + (uint64_t)(2 * j), idesc,
+                                       FIRST ? (ks0 + j > 0 ? 1u : 0u) : 1u, FIRST ? (ks0 + j >= n_main ? 1u : 0u) : 1u);
+                }
                 d_main = (d_main == main_hi) ? main_lo : d_main + (uint32_t)stride;
               }
             }
-            umma_commit_warp(bar_ae + 8u * sa);
+            if (PAIR) umma_commit_pair_warp(bar_ae + 8u * sa);
+            else umma_commit_warp(bar_ae + 8u * sa);
             if (++sa == nas) { sa = 0; pa ^= 1u; }
           }
         }
-        umma_commit_warp(bar_be + 8u * sb);
+        if (PAIR) umma_commit_pair_warp(bar_be + 8u * sb);
+        else umma_commit_warp(bar_be + 8u * sb);
         if (++sb == nsb) { sb = 0; pb ^= 1u; }
       };
       const int nkb_full = nks >> 2;       // k-blocks whose four k-steps all carry data
@@ -327,7 +399,8 @@ tc_tma_gemm_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapA, 
         if (kb == 0) block(std::true_type{}, nks - kb * 4, 0);
         else block(std::false_type{}, nks - kb * 4, kb * 4);
       }
-      umma_commit_warp(smem_u32(&bar_done));
+      if (PAIR) umma_commit_pair_warp(smem_u32(&bar_done));
+      else umma_commit_warp(smem_u32(&bar_done));
     }
     __syncwarp();
   } else {
@@ -386,7 +459,7 @@ tc_tma_gemm_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapA, 
       }
     } else if (BT) {
       // ===== B warps: the raw tile TMA wrote (SWIZZLE_128B) is split in place: hi over the raw bytes, lo into the twin =====
-      const int f4_used = ((n_valid + 7) & ~7) * 8;   // whole 8-row swizzle atoms that hold stored rows
+      const int f4_used = (((PAIR ? hp : n_valid) + 7) & ~7) * 8;   // whole 8-row swizzle atoms that hold stored rows
       constexpr int IT = (TC_BM * 8 + LT - 1) / LT;   // float4 items per thread (bn <= 128 rows x 8)
       RingPos rb = {0, 0};
       for (int kb = 0; kb < nkb_feed; ++kb) {
@@ -486,7 +559,8 @@ tc_tma_gemm_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapA, 
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] += __uint_as_float(r1[j]);
     };
-    auto chunk_ok = [&](int c) { return c < nch && c * 16 < n_valid; };
+    // PAIR: batch row r sits in accumulator column r (r < hp, the leader's lines) or bh + r - hp (the peer's lines)
+    auto chunk_ok = [&](int c) { return c < nch && (PAIR || c * 16 < n_valid); };
     // accumulators to shared ([n][m], through the idle operand stages), then float4 rows of the output
     float* T = reinterpret_cast<float*>(smem);
     for (int c = part; chunk_ok(c); c += PARTS) {
@@ -521,7 +595,9 @@ tc_tma_gemm_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapA, 
       for (int u = 0; u < UNR; ++u) {
         const int i = i0 + u * ET;
         if (i < items && mq < m4_valid) {
-          float4 o = *reinterpret_cast<const float4*>(T + (i >> 5) * TC_BM + mq * 4);
+          const int r = i >> 5;
+          const int col = (PAIR && r >= hp) ? r - hp + bh : r;
+          float4 o = *reinterpret_cast<const float4*>(T + col * TC_BM + mq * 4);
           if (EPI == EPI_FWD) {
             o.x = act_fwd(o.x + b4.x, p.act, p.slope); o.y = act_fwd(o.y + b4.y, p.act, p.slope);
             o.z = act_fwd(o.z + b4.z, p.act, p.slope); o.w = act_fwd(o.w + b4.w, p.act, p.slope);
@@ -537,8 +613,13 @@ tc_tma_gemm_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapA, 
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == MMAW) tmem_dealloc(tmem_d, TC_TMEM_COLS);
+  if (PAIR) {
+    cluster_sync_all();          // neither CTA leaves (or frees TMEM) while the other may still be read or signalled
+    if (warp == MMAW) tmem_dealloc_pair(tmem_d, TC_TMEM_COLS);
+  } else {
+    __syncthreads();
+    if (warp == MMAW) tmem_dealloc(tmem_d, TC_TMEM_COLS);
+  }
 }
 
 // ---- host side ----
@@ -599,16 +680,34 @@ static inline bool tct_plan(int N, int K, int rows0, int* bn_out, int* per_out, 
   return false;
 }
 
-template <bool A_KMAJOR, int EPI, int LWB, bool BT>
+template <bool A_KMAJOR, int EPI, int LWB, bool BT, bool PAIR>
 static inline void launch_tc_tma_inst(const TcParams& p, const CUtensorMap& mapA, const CUtensorMap& mapAt, const CUtensorMap& mapB0,
                                       const CUtensorMap& mapB1, dim3 grid, size_t smem, cudaStream_t stream, cudaError_t* err) {
   static unsigned long long attr = 0;
   if (first_use_on_device(attr)) {
-    *err = cudaFuncSetAttribute(tc_tma_gemm_kernel<A_KMAJOR, EPI, LWB, BT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    *err = cudaFuncSetAttribute(tc_tma_gemm_kernel<A_KMAJOR, EPI, LWB, BT, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)TC_SMEM_BUDGET);
     if (*err != cudaSuccess) return;
   }
-  tc_tma_gemm_kernel<A_KMAJOR, EPI, LWB, BT><<<grid, (LWB + 10) * 32, smem, stream>>>(p, mapA, mapAt, mapB0, mapB1);
+  if (PAIR) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3((LWB + 10) * 32, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    *err = cudaLaunchKernelEx(&cfg, tc_tma_gemm_kernel<A_KMAJOR, EPI, LWB, BT, PAIR>, p, mapA, mapAt, mapB0, mapB1);
+    count_launch();
+    if (*err == cudaSuccess) *err = cudaGetLastError();
+    return;
+  }
+  tc_tma_gemm_kernel<A_KMAJOR, EPI, LWB, BT, PAIR><<<grid, (LWB + 10) * 32, smem, stream>>>(p, mapA, mapAt, mapB0, mapB1);
   count_launch();
   *err = cudaGetLastError();
 }
@@ -616,17 +715,18 @@ static inline void launch_tc_tma_inst(const TcParams& p, const CUtensorMap& mapA
 // true: launched (or failed with *err set); false: not applicable (the caller uses the shared-memory-operand kernels).
 // A must be the weight matrix of a packed bank: one dense [lines][ld] matrix per group (single RowMap).
 // No TMA box may reach beyond the rows of its matrix (see the kernel): ragged last tiles of A use a tail map, B goes by TMA only
-// when its boxes (n_per rows x 32 k) tile every source exactly, and K is a multiple of 32 (K = 100, the generators' first
-// layer, stays on the shared-memory-operand kernels).
+// when its boxes (n_per rows x 32 k) tile every source exactly, and K is a multiple of 16.
 template <bool A_KMAJOR, int EPI>
 static inline bool launch_tc_tma(TcParams p, int G, cudaStream_t stream, cudaError_t* err) {
   if (!(tc_tune() & 131072)) return false;
   if (G <= 0 || p.M <= 0 || p.N <= 0) return false;
   if (!p.c_vec || !p.A.vec || !p.B.vec || p.A.rows0 != 0x7fffffff) return false;
   if (p.K < 2 * TC_BK || p.M < 64) return false;
-  // forward: no box column beyond K. Data gradient: the k-steps cover K exactly; box columns beyond `in` (in % 128 != 0) belong
+  // forward: box columns beyond K (K % 32 != 0: the last k-block of K = 784) are zero-filled; measured safe with the operands
+  // at the very end of their allocations for K % 16 == 0 (profiles/tma_repro.py), while K = 100 faults there -- the
+  // generators' first layer stays on the shared-memory-operand kernels. Data gradient: the k-steps cover K exactly; box columns beyond `in` (in % 128 != 0) belong
   // to the next row of W, for the last row to the bias that follows W in the packed row (out >= 128 floats cover them)
-  if (A_KMAJOR ? (p.K % TC_BK != 0) : (p.K % 8 != 0 || (p.M % TC_BM != 0 && p.K < TC_BM))) return false;
+  if (A_KMAJOR ? (p.K % 16 != 0) : (p.K % 8 != 0 || (p.M % TC_BM != 0 && p.K < TC_BM))) return false;
   // the weight matrix as the tensor map sees it: forward A = W[out = M][in = K]; data gradient A = W[out = K][in = M]
   const int w_in = A_KMAJOR ? p.K : p.M, w_out = A_KMAJOR ? p.M : p.K;
   if (p.A.ld != w_in) return false;
@@ -644,11 +744,15 @@ static inline bool launch_tc_tma(TcParams p, int G, cudaStream_t stream, cudaErr
   }
   // B by TMA: every source a dense [rows][ld] matrix per group that the n_per-row boxes tile exactly, K % 32 == 0
   // (tune bit 524288 keeps the register path for comparisons)
-  bool bt = !(tc_tune() & 524288) && (p.K % TC_BK == 0);
+  bool bt = !(tc_tune() & 524288) && (p.K % 16 == 0);
   const int rows_b0 = dual ? p.B.rows0 : p.N, rows_b1 = dual ? p.N - p.B.rows0 : 0;
   if (rows_b0 % per || rows_b1 % per) bt = false;
-  if (bt) bt = tct_make_map(&mapB0, p.B.base0, p.K, rows_b0, p.B.ld, p.B.gstride0, TC_BK, per, true);
-  if (bt && dual) bt = tct_make_map(&mapB1, p.B.base1, p.K, rows_b1, p.B.ld, p.B.gstride1, TC_BK, per, true);
+  // CTA pairs (tune bit 4194304 switches them off): B by TMA in two halves, at least two M tiles
+  // (opt-in, tune bit 8388608: measured slower than the one-CTA kernel -- profiles/tma_pair_r2.log)
+  const bool pair = bt && (tc_tune() & 8388608) && (per % 2 == 0) && p.M > TC_BM;
+  const int box_b = pair ? per / 2 : per;
+  if (bt) bt = tct_make_map(&mapB0, p.B.base0, p.K, rows_b0, p.B.ld, p.B.gstride0, TC_BK, box_b, true);
+  if (bt && dual) bt = tct_make_map(&mapB1, p.B.base1, p.K, rows_b1, p.B.ld, p.B.gstride1, TC_BK, box_b, true);
   if (bt && !dual) mapB1 = mapB0;
   if (!bt) { mapB0 = mapA; mapB1 = mapA; }
   p.bn = bn;
@@ -663,14 +767,17 @@ static inline bool launch_tc_tma(TcParams p, int G, cudaStream_t stream, cudaErr
   const size_t t_bytes = (size_t)bn * TC_BM * 4;
   if (smem < t_bytes) smem = t_bytes;
   smem += 1024;
-  dim3 grid((p.N + per - 1) / per, (p.M + TC_BM - 1) / TC_BM, G);
+  const int m_tiles = (p.M + TC_BM - 1) / TC_BM;
+  dim3 grid((p.N + per - 1) / per, m_tiles, G);
+  if (pair && bt) grid = dim3((m_tiles + 1) / 2 * 2, (p.N + per - 1) / per, G);   // the pair lies along x
   *err = cudaSuccess;
   static const bool dbg = getenv("CGL_DEBUG_TMA") != nullptr;
   if (dbg)
     fprintf(stderr, "tc_tma<%d,%d> G=%d M=%d N=%d K=%d bn=%d per=%d n_main=%d nas=%d nsb=%d bt=%d dual=%d rows0=%d tail=%d\n",
-            (int)A_KMAJOR, EPI, G, p.M, p.N, p.K, bn, per, n_main, nas, p.n_stages, (int)bt, (int)dual, p.B.rows0, tail_rows);
-  if (bt) launch_tc_tma_inst<A_KMAJOR, EPI, 8, true>(p, mapA, mapAt, mapB0, mapB1, grid, smem, stream, err);
-  else launch_tc_tma_inst<A_KMAJOR, EPI, 8, false>(p, mapA, mapAt, mapB0, mapB1, grid, smem, stream, err);
+            (int)A_KMAJOR, EPI, G, p.M, p.N, p.K, bn, per, n_main, nas, p.n_stages, (int)bt + (int)(bt && pair), (int)dual, p.B.rows0, tail_rows);
+  if (bt && pair) launch_tc_tma_inst<A_KMAJOR, EPI, 8, true, true>(p, mapA, mapAt, mapB0, mapB1, grid, smem, stream, err);
+  else if (bt) launch_tc_tma_inst<A_KMAJOR, EPI, 8, true, false>(p, mapA, mapAt, mapB0, mapB1, grid, smem, stream, err);
+  else launch_tc_tma_inst<A_KMAJOR, EPI, 8, false, false>(p, mapA, mapAt, mapB0, mapB1, grid, smem, stream, err);
   return true;
 }
 
