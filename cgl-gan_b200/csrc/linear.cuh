@@ -13,6 +13,7 @@
 #include "tc_pair.cuh"
 #include "tc_sweep.cuh"
 #include "tc_tma.cuh"
+#include "tc_tma_persist.cuh"
 
 namespace cgl {
 
@@ -90,6 +91,7 @@ static inline cudaError_t run_linear_fwd(int G, int rows, int in, int out, const
     p.bias_base = (b_off >= 0) ? params : nullptr; p.bias_gstride = ldp; p.bias_idx = ids; p.bias_off = b_off;
     p.act = act; p.slope = slope;
     cudaError_t pe = cudaSuccess;
+    if (launch_tc_tma_persistent<true, EPI_FWD>(p, G, st, &pe)) return pe;
     if (launch_tc_tma<true, EPI_FWD>(p, G, st, &pe)) return pe;
     if (launch_tc_sweep<true, true, EPI_FWD>(p, G, st, &pe)) return pe;
     if ((tc_tune() & 256) && launch_tc_pair<true, EPI_FWD>(p, G, st, &pe)) return pe;
@@ -128,6 +130,7 @@ static inline cudaError_t run_linear_bwd_data(int G, int rows, int in, int out, 
                (!saved || (aligned16(saved) && saved_gstride % 4 == 0))) ? 1 : 0;
     p.saved = saved; p.saved_gstride = saved_gstride; p.act = act; p.slope = slope;
     cudaError_t pe = cudaSuccess;
+    if (launch_tc_tma_persistent<false, EPI_BWD_DATA>(p, G, st, &pe)) return pe;
     if (launch_tc_tma<false, EPI_BWD_DATA>(p, G, st, &pe)) return pe;
     if (launch_tc_sweep<false, true, EPI_BWD_DATA>(p, G, st, &pe)) return pe;                  // saved == NULL: plain store
     if ((tc_tune() & 512) && launch_tc_pair<false, EPI_BWD_DATA>(p, G, st, &pe)) return pe;

@@ -310,7 +310,8 @@ struct TcParams {
              // 16384 / 32768 = persistent kernel with the lean 16-warp loader loop (tc_sweep.cuh) for forward / data gradient,
              // 65536 = CTA pairs also for an odd number of M tiles,
              // 131072 = TMA-fed kernel with the weights in TMEM (tc_tma.cuh) for forward / data gradient (524288: its B operand
-             // through registers instead of TMA, 1048576: its one-thread MMA issue loop; 4096 / 8192: its ablations)
+             // through registers instead of TMA, 1048576: its one-thread MMA issue loop; 4096 / 8192: its ablations; 2097152: only the
+             // hi*hi regions the accumulation cap needs; 8388608: CTA pairs; 16777216: persistent variant, tc_tma_persist.cuh)
 };
 
 // TMEM plan (512 columns, 1 CTA per SM). The tensor core TRUNCATES when it adds into an fp32

@@ -722,6 +722,10 @@ static inline bool launch_tc_tma(TcParams p, int G, cudaStream_t stream, cudaErr
   if (G <= 0 || p.M <= 0 || p.N <= 0) return false;
   if (!p.c_vec || !p.A.vec || !p.B.vec || p.A.rows0 != 0x7fffffff) return false;
   if (p.K < 2 * TC_BK || p.M < 64) return false;
+  // short K (<= 43 k-steps: the 128 x 256 layer of the 2DMG discriminator, the generator trunks, the data gradient of 512 <- 256):
+  // a tile is 2 - 8 k-blocks between its set-up and its epilogue, and the two-CTAs-per-SM variant of tc_gemm.cuh (one accumulation
+  // region, 256 TMEM columns) overlaps those phases -- measured 0.64 against 0.70 ms on the 512 <- 256 data gradient
+  if ((tc_tune() & 1024) && (p.K + 7) / 8 <= TC_MAX_ACCUM) return false;
   // forward: box columns beyond K (K % 32 != 0: the last k-block of K = 784) are zero-filled; measured safe with the operands
   // at the very end of their allocations for K % 16 == 0 (profiles/tma_repro.py), while K = 100 faults there -- the
   // generators' first layer stays on the shared-memory-operand kernels. Data gradient: the k-steps cover K exactly; box columns beyond `in` (in % 128 != 0) belong
