@@ -1,7 +1,7 @@
 """DRAM traffic per launch of every engine kernel class, from one ncu capture of a few bench rounds:
     ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv \
         --log-file gpurun_out/traffic_r1.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline
-    python profiles/summarize_traffic.py gpurun_out/traffic_r1.csv mnist > profiles/traffic_r1.json   (merges datasets)
+    python profiles/summarize_traffic.py gpurun_out/traffic_r2.csv mnist [traffic_r2.json] > /tmp/t.json && mv /tmp/t.json profiles/traffic_r2.json   (merges datasets)
 The classes are bench.py's (cgl_profile_* tags); a class launch = one Linear product (the weight-gradient class
 includes its bias-gradient kernel, as the event pairs in bench.py do)."""
 import csv
@@ -13,7 +13,11 @@ from collections import defaultdict
 
 
 def classify(name):
-    m = re.search(r"tc_(?:grouped|persistent)_gemm_kernel<(?:\(bool\))?(\d), (?:\(bool\))?(\d), (?:\(int\))?(\d)", name)
+    # the TMA-fed kernels and the CTA-pair kernel: template arguments (A_KMAJOR, EPI, ...)
+    t = re.search(r"tc_(?:tma_gemm|tma_persistent|pair_gemm)_kernel<(?:\(bool\))?(\d), (?:\(int\))?(\d)", name)
+    if t:
+        return ("linear_fwd[tcgen05]" if int(t.group(2)) == 0 else "linear_bwd_data[tcgen05]"), True
+    m = re.search(r"tc_(?:grouped|persistent|sweep)_gemm_kernel<(?:\(bool\))?(\d), (?:\(bool\))?(\d), (?:\(int\))?(\d)", name)
     tag = "[tcgen05]"
     if not m:
         m = re.search(r"cgl::grouped_gemm_kernel<(?:\(bool\))?(\d), (?:\(bool\))?(\d), (?:\(int\))?(\d)", name)
@@ -62,7 +66,7 @@ def main(path, dataset):
         a[1] += met.get("dram__bytes_read.sum", 0.0)
         a[2] += met.get("dram__bytes_write.sum", 0.0)
         a[3] += met.get("gpu__time_duration.sum", 0.0)
-    out_path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "traffic_r1.json")
+    out_path = os.path.join(os.path.dirname(os.path.abspath(__file__)), sys.argv[3] if len(sys.argv) > 3 else "traffic_r2.json")
     doc = json.load(open(out_path)) if os.path.exists(out_path) else {}
     doc[dataset] = {c: {"dram_bytes_per_launch": (a[1] + a[2]) / max(a[0], 1), "dram_read_bytes_per_launch": a[1] / max(a[0], 1),
                         "dram_write_bytes_per_launch": a[2] / max(a[0], 1), "launches_captured": a[0],
