@@ -73,8 +73,26 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+#ifndef TC_WAIT_MODE
+#define TC_WAIT_MODE 0   // 0: try_wait with a suspend-time hint; 1: try_wait with the default time limit; 2: test_wait (pure polling)
+#endif
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok = 0;
+#if TC_WAIT_MODE == 1
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+#elif TC_WAIT_MODE == 2
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+#endif
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
@@ -86,6 +104,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
+#if TC_WAIT_MODE != 0
+  const long long c0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - c0 > 4000000000ll) __trap();   // ~2 s: a lost arrival must fail loudly, not hang the GPU
+  }
+  return;
+#endif
   unsigned long long t0;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
   while (!mbar_try_wait(bar, parity)) {
@@ -311,7 +336,12 @@ struct TcParams {
              // 65536 = CTA pairs also for an odd number of M tiles,
              // 131072 = TMA-fed kernel with the weights in TMEM (tc_tma.cuh) for forward / data gradient (524288: its B operand
              // through registers instead of TMA, 1048576: its one-thread MMA issue loop; 4096 / 8192: its ablations; 2097152: only the
-             // hi*hi regions the accumulation cap needs; 8388608: CTA pairs; 16777216: persistent variant, tc_tma_persist.cuh)
+             // hi*hi regions the accumulation cap needs; 8388608: CTA pairs; 16777216: persistent variant, tc_tma_persist.cuh;
+             // 33554432: the TMA-written batch tile stays in place as hi (the tensor core truncates), only lo is stored;
+             // 4: TWO issuing warps that take the k-blocks in turn (token barrier); 2: look-ahead barrier tests in the (single)
+             // issuing warp; 262144: A converters load the next k-block under their TMEM stores; bring-up ablations of the
+             // feed: 67108864 / 134217728 no B / A transfers, 268435456 / 536870912 A converters / B warps run their barrier
+             // protocol only, 1073741824 two hi*hi regions at any K (timing only) -- profiles/tma_feed_abl_r2.log)
 };
 
 // TMEM plan (512 columns, 1 CTA per SM). The tensor core TRUNCATES when it adds into an fp32

@@ -90,6 +90,24 @@ __device__ __forceinline__ void umma_kstep_ts_warp(uint32_t d_corr, uint32_t d_m
       ::"r"(d_corr), "r"(d_main), "r"(a_hi), "r"(a_lo), "l"(dbh), "l"(dbl), "r"(idesc), "r"(acc_corr), "r"(acc_main)
       : "memory");
 }
+// one arrival from a converged warp (the elected lane arrives; no divergent region around the tcgen05 issue loop)
+__device__ __forceinline__ void mbar_arrive_elect(uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e mbarrier.arrive.shared::cta.b64 _, [%0];\n\t}"
+      ::"r"(bar) : "memory");
+}
+// non-blocking test of a barrier phase (acquire, like the waits)
+__device__ __forceinline__ uint32_t mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok;
+}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
@@ -134,6 +152,18 @@ struct RingPos {
   }
 };
 
+// -DTCT_PROFILE (variant builds for profiles/tma_agents.py): CTA (0, 0, g) records in g_tc_timeline[g * 32 + i] clock64 stamps
+// (0 entry, 1 set-up done, 2 / 3 MMA loop start / end, 4 / 5 epilogue start / end) and the cycles its agents spent inside their
+// barrier waits (6 MMA warp on b_full, 7 on a_full, 8 TMA thread on b_empty, 9 on raw_empty, 10 converter warp 0 on raw_full,
+// 11 on a_empty, 12 B warp 0 on b_raw) and in their whole loops (13 converter warp 0, 14 B warp 0, 15 TMA thread); 16 / 17: the
+// MMA warp's cycles issuing tcgen05.mma / tcgen05.commit
+#ifdef TCT_PROFILE
+#define TCT_TIMED(acc, stmt) do { const long long _c0 = clock64(); stmt; acc += clock64() - _c0; } while (0)
+#define TCT_PUT(i, v) do { if (prof) g_tc_timeline[blockIdx.z * 32 + (i)] = (v); } while (0)
+#else
+#define TCT_TIMED(acc, stmt) do { stmt; } while (0)
+#define TCT_PUT(i, v) do { } while (0)
+#endif
 // B is K-major (lines = batch rows). EPI: EPI_FWD (A K-major: forward) / EPI_BWD_DATA (A MN-major: data gradient; saved == NULL
 // stores the plain product). LWB = loader warps (multiple of 4).
 // PAIR (needs BT): two CTAs of a cluster (adjacent M tiles of one group) run every MMA together (cta_group::2, issued by the CTA
@@ -142,12 +172,13 @@ struct RingPos {
 // one-CTA kernel (profiles/tma_ablate_r2.log). The peer's MMA warp forwards its full barriers to the leader (one remote
 // arrive each); the commits arrive on the empty barriers of both CTAs. An odd number of M tiles adds a CTA without rows.
 template <bool A_KMAJOR, int EPI, int LWB, bool BT, bool PAIR>
-__global__ void __launch_bounds__((LWB + 10) * 32, 1)
+__global__ void __launch_bounds__((LWB + 11) * 32, 1)
 tc_tma_gemm_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapAt,
                    const __grid_constant__ CUtensorMap tmapB0, const __grid_constant__ CUtensorMap tmapB1) {
   constexpr int CW0 = LWB;             // first converter warp
   constexpr int MMAW = LWB + 8;
   constexpr int TMAW = LWB + 9;
+  constexpr int MMAW2 = LWB + 10;      // second issuing warp (dual issue: the k-blocks alternate between the two)
   constexpr int LT = LWB * 32;         // loader threads
   constexpr int ET = (LWB + 8) * 32;   // epilogue threads (B warps + A converters)
   constexpr int BKT = 32;
@@ -155,7 +186,7 @@ tc_tma_gemm_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapA, 
   extern __shared__ __align__(1024) char tc_smem[];
   __shared__ __align__(8) unsigned long long bar_raw_full[TCT_NRAW];
   __shared__ __align__(8) unsigned long long bar_raw_empty[TCT_NRAW];
-  __shared__ __align__(8) unsigned long long bar_a_full[TCT_MAX_AS];
+  __shared__ __align__(8) unsigned long long bar_a_full[2 * TCT_MAX_AS];   // ring of abars barriers over the nas stages (below)
   __shared__ __align__(8) unsigned long long bar_a_empty[TCT_MAX_AS];
   __shared__ __align__(8) unsigned long long bar_b_raw[TC_MAX_STAGES];
   __shared__ __align__(8) unsigned long long bar_b_full[TC_MAX_STAGES];
@@ -163,10 +194,16 @@ tc_tma_gemm_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapA, 
   __shared__ __align__(8) unsigned long long bar_peer_a[TCT_MAX_AS];     // PAIR, leader: the peer's A stage is full
   __shared__ __align__(8) unsigned long long bar_peer_b[TC_MAX_STAGES];  // PAIR, leader: the peer's B stage is full
   __shared__ __align__(8) unsigned long long bar_done;
+  __shared__ __align__(8) unsigned long long bar_tok[2];                 // dual issue: warp i may issue its next k-block
   __shared__ uint32_t tmem_slot;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = blockIdx.z;
+#ifdef TCT_PROFILE
+  const bool prof = g_tc_timeline != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0;
+  long long w0 = 0, w1 = 0, w2 = 0, w3 = 0, loop0 = 0;
+  if (tid == 0) TCT_PUT(0, clock64());
+#endif
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
   // (a kernel that uses cta_group::2 is only accepted with an even cluster width in x: the pair lies along x)
   const int m0 = (PAIR ? blockIdx.x : blockIdx.y) * TC_BM;
@@ -189,14 +226,27 @@ tc_tma_gemm_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapA, 
   const int nkb = (p.K + BKT - 1) / BKT;
   const int nks = (p.K + 7) >> 3;
   const int rowid = p.A.idx0 ? p.A.idx0[g] : g;             // bank row of this group's weights
+  // Dual issue (experiment, tune bit 4): the issuing warp is ONE dependent instruction chain per k-block -- three barrier
+  // waits (~130-170 clk each, even on a completed phase), three tcgen05.fence, twelve tcgen05.mma (~45 clk each to issue) and
+  // three tcgen05.commit (~55 clk). Two warps take the k-blocks in turn; a token barrier hands the right to issue from one to
+  // the other, so the MMAs still enter the tensor pipe in k order (bit-identical results) while each warp's waits, fences and
+  // commits run under the other's MMAs. Measured (profiles/tma_dual_r2.log): correct, and 15 - 20 % SLOWER with two A stages
+  // (the wait for both halves of a k-block before the token lengthens the A-stage round trip), 2 % faster with four.
+  const bool dual_issue = !PAIR && !(p.tune & 1048576) && (p.tune & 4) && p.n_stages >= 2;
+  // The "A stage full" barriers form a ring of abars = 2 * nas barriers over the nas stages (use u of the ring: stage u % nas,
+  // barrier u % abars): with two issuing warps the waits for k-block kb + 1 start before those for kb have returned, and with
+  // ONE barrier per stage a wait on the next phase of a barrier whose current phase is still open returns at once (a parity
+  // wait cannot tell phase n + 1 from phase n - 1). Consecutive k-blocks never share a barrier this way (nas >= 2 stages of
+  // 16 k = at least one k-block; the B ring has n_stages >= 2 barriers of its own).
+  const int abars = PAIR ? p.tmem_cols : 2 * p.tmem_cols;
 
   if (tid == 0) {
     for (int i = 0; i < TCT_NRAW; ++i) {
       mbar_init(smem_u32(&bar_raw_full[i]), 1);
       mbar_init(smem_u32(&bar_raw_empty[i]), 8);
     }
+    for (int i = 0; i < 2 * TCT_MAX_AS; ++i) mbar_init(smem_u32(&bar_a_full[i]), 4);
     for (int i = 0; i < TCT_MAX_AS; ++i) {
-      mbar_init(smem_u32(&bar_a_full[i]), 4);
       mbar_init(smem_u32(&bar_a_empty[i]), 1);
       mbar_init(smem_u32(&bar_peer_a[i]), 1);
     }
@@ -206,7 +256,9 @@ tc_tma_gemm_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapA, 
       mbar_init(smem_u32(&bar_b_empty[i]), 1);
       mbar_init(smem_u32(&bar_peer_b[i]), 1);
     }
-    mbar_init(smem_u32(&bar_done), 1);
+    mbar_init(smem_u32(&bar_done), dual_issue ? 2 : 1);
+    mbar_init(smem_u32(&bar_tok[0]), 1);
+    mbar_init(smem_u32(&bar_tok[1]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == MMAW) {
@@ -217,6 +269,10 @@ tc_tma_gemm_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapA, 
   if (PAIR) cluster_sync_all();   // barriers initialised and TMEM allocated in both CTAs before anything is signalled
   else __syncthreads();
   tc_fence_after();
+#ifdef TCT_PROFILE
+  if (tid == 0) TCT_PUT(1, clock64());
+  loop0 = clock64();
+#endif
   const uint32_t tmem_d = tmem_slot;
   // bring-up ablations (CGL_TUNE): 4096 = MMAs only (nothing is fed, the MMA thread never waits: what the tensor pipe
   // alone costs), 8192 = no MMAs (what feeding alone costs)
@@ -238,15 +294,22 @@ tc_tma_gemm_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapA, 
         else b_grp = p.B.idx0 ? p.B.idx0[g] : g;
       }
       RingPos r = {0, 0}, rb = {0, 0};
+      // bring-up ablations (results are garbage): 67108864 = no B transfers, 134217728 = no A transfers -- what the feed costs
+      // without the bytes of one operand crossing L2 -> SM
+      const bool skip_b = (p.tune & 67108864) != 0, skip_a = (p.tune & 134217728) != 0;
       for (int kb = 0; kb < nkb_feed; ++kb) {
         if (BT) {
-          if (rb.round > 0) mbar_wait(smem_u32(&bar_b_empty[rb.slot]), (rb.round - 1) & 1u);   // the MMAs that read it are done
+          if (rb.round > 0) TCT_TIMED(w0, mbar_wait(smem_u32(&bar_b_empty[rb.slot]), (rb.round - 1) & 1u));   // the MMAs that read it are done
           const uint32_t bbar = smem_u32(&bar_b_raw[rb.slot]);
-          mbar_arrive_expect_tx(bbar, b_tx);
-          tma_load_3d(smem_u32(smem_b + (size_t)rb.slot * bstage_bytes), tmapB, kb * BKT, b_row, b_grp, bbar);
+          if (skip_b) {                      // bring-up ablation: the stage is declared full without a transfer
+            mbar_arrive(bbar);
+          } else {
+            mbar_arrive_expect_tx(bbar, b_tx);
+            tma_load_3d(smem_u32(smem_b + (size_t)rb.slot * bstage_bytes), tmapB, kb * BKT, b_row, b_grp, bbar);
+          }
           rb.next(nsb);
         }
-        if (r.round > 0) mbar_wait(smem_u32(&bar_raw_empty[r.slot]), (r.round - 1) & 1u);
+        if (r.round > 0) TCT_TIMED(w1, mbar_wait(smem_u32(&bar_raw_empty[r.slot]), (r.round - 1) & 1u));
         const uint32_t bar = smem_u32(&bar_raw_full[r.slot]);
         const uint32_t dst = smem_u32(smem_raw + (size_t)r.slot * TCT_RAW_BYTES);
         // A box never reaches beyond the last ROW of the weight matrix (the ragged last tile uses the tail map, whose box
@@ -254,7 +317,7 @@ tc_tma_gemm_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapA, 
         // (profiles/tma_repro.py faults with the operand at the end of its allocation), and behind the last matrix of the
         // last bank row there may be nothing mapped. Rows of the stage the tail box leaves unwritten only reach
         // accumulator rows m >= M (forward) or k-steps that are never issued (data gradient, K % 8 == 0).
-        if (PAIR && m0 >= p.M) {             // the CTA that completes an odd number of M tiles: no rows, nothing to fetch
+        if ((PAIR && m0 >= p.M) || skip_a) {   // the CTA that completes an odd number of M tiles: no rows, nothing to fetch
           mbar_arrive(bar);
         } else if (A_KMAJOR) {               // box (32 k, 128 | M % 128 rows m): 128-byte rows, SWIZZLE_128B
           const bool tail = m0 + TC_BM > p.M;
@@ -267,17 +330,22 @@ tc_tma_gemm_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapA, 
         }
         r.next(TCT_NRAW);
       }
+#ifdef TCT_PROFILE
+      TCT_PUT(8, w0); TCT_PUT(9, w1); TCT_PUT(15, clock64() - loop0);
+#endif
     }
     __syncwarp();
-  } else if (warp == MMAW) {
+  } else if (warp == MMAW || warp == MMAW2) {
     // ===== MMA issuer: the whole warp runs the loop converged, the elected lane issues (see umma_tf32_ts_warp) =====
     // The loop is the critical instruction stream of the kernel (one warp, dependent issue): the first k-block (accumulate
     // flags) and a ragged last one (k-steps beyond K) are peeled off so that the blocks in between are branch-free.
-    if (!PAIR && (p.tune & 1048576)) {
+    if (warp == MMAW2 && !dual_issue) {
+      // (idle: one issuing warp)
+    } else if (!PAIR && (p.tune & 1048576)) {
       // (comparison: the one-thread issue loop this kernel started with -- ~135 clk per MMA)
       if (lane == 0) {
         const uint32_t idesc = umma_idesc_tf32(false, false, bn);
-        RingPos rb = {0, 0}, ra = {0, 0};
+        RingPos rb = {0, 0}, ra = {0, 0}, rf = {0, 0};   // B stage, A stage, "A stage full" barrier
         int ks = 0, reg = 0;
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(smem_u32(&bar_b_full[rb.slot]), rb.round & 1u);
@@ -285,7 +353,8 @@ tc_tma_gemm_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapA, 
           const uint32_t sb_hi = smem_u32(smem_b + (size_t)rb.slot * bstage_bytes);
           for (int h = 0; h < 2; ++h) {
             if (ks < nks) {
-              mbar_wait(smem_u32(&bar_a_full[ra.slot]), ra.round & 1u);
+              mbar_wait(smem_u32(&bar_a_full[rf.slot]), rf.round & 1u);
+              rf.next(abars);
               tc_fence_after();
               const uint32_t ta = tmem_d + a_col0 + (uint32_t)(ra.slot * 32);
               for (int jj = 0; jj < 2; ++jj) {
@@ -344,13 +413,23 @@ tc_tma_gemm_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapA, 
       const uint32_t bar_af = smem_u32(&bar_a_full[0]), bar_ae = smem_u32(&bar_a_empty[0]);
       const uint32_t bar_pa = smem_u32(&bar_peer_a[0]), bar_pb = smem_u32(&bar_peer_b[0]);
       uint32_t d_main = main_lo;           // main region of the next k-step
-      int sb = 0, sa = 0;
-      uint32_t pb = 0, pa = 0;             // parities of the current rounds
+      int sb = 0, sa = 0, fa = 0;          // B stage, A stage, "A stage full" barrier of the next use
+      uint32_t pb = 0, pa = 0;             // parities of the current rounds (pa: of the a_full barrier ring)
+      const bool probe = !PAIR && !dual_issue && (p.tune & 2);    // tune bit 2: look-ahead barrier tests (measured: the issuing warp's wait time
+                                                   // halves, the k-block period does not move -- profiles/tma_agents_r2.log)
+      uint32_t a_ok = 0, b_ok = 0;                 // the next A / B stage was already full when it was tested
+      const int me = (warp == MMAW) ? 0 : 1;       // dual issue: this warp issues the k-blocks kb % 2 == me
+      const uint32_t bar_tk = smem_u32(&bar_tok[0]);
+      uint32_t tok_par = 0;
+      bool waited = false, pass_token = false;
+#ifdef TCT_PROFILE
+      long long w4 = 0;
+#endif
       // one 32-wide k-block: FIRST = accumulate flags of the first k-steps, KS = k-steps that carry data (1..4)
       auto block = [&](auto first_c, int nks_here, int ks0) {
         constexpr bool FIRST = decltype(first_c)::value;
-        if (!mma_only) {
-          mbar_wait(bar_bf + 8u * sb, pb);
+        if (!mma_only && !waited) {
+          if (!__all_sync(0xffffffffu, b_ok)) TCT_TIMED(w0, mbar_wait(bar_bf + 8u * sb, pb));
           if (PAIR) mbar_wait_cluster(bar_pb + 8u * sb, pb);
         }
         tc_fence_after();
@@ -360,11 +439,26 @@ tc_tma_gemm_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapA, 
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           if (h * 2 < nks_here) {
-            if (!mma_only) {
-              mbar_wait(bar_af + 8u * sa, pa);
+            if (!mma_only && !waited) {
+              if (!__all_sync(0xffffffffu, a_ok)) TCT_TIMED(w1, mbar_wait(bar_af + 8u * fa, pa));
             }
             tc_fence_after();
+            if (probe && !mma_only) {
+              // (experiment) The issuing warp is one dependent chain (wait -> MMAs -> commit -> wait ...), and a barrier wait costs
+              // it ~100 clk even when the phase completed long ago. Here the NEXT barriers are tested now, without blocking, and
+              // the answers arrive under the MMAs issued below: a stage that was already full is then entered without a wait. The answers are only looked at where the wait would be (a use right here would stall the
+              // warp for the test's latency); warp-uniform through a vote there: a lane that saw "not yet" sends all into the wait.
+              const int fan = (fa + 1 == abars) ? 0 : fa + 1;
+              a_ok = mbar_test(bar_af + 8u * fan, (fa + 1 == abars) ? (pa ^ 1u) : pa);
+              if (h == 1) {
+                const int sbn = (sb + 1 == nsb) ? 0 : sb + 1;
+                b_ok = mbar_test(bar_bf + 8u * sbn, (sb + 1 == nsb) ? (pb ^ 1u) : pb);
+              }
+            }
             const uint32_t ta = tmem_a0 + (uint32_t)(sa * 32);
+#ifdef TCT_PROFILE
+            const long long cm0 = clock64();
+#endif
 #pragma unroll
             for (int jj = 0; jj < 2; ++jj) {
               const int j = h * 2 + jj;
@@ -382,25 +476,81 @@ tc_tma_gemm_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapA, 
                 d_main = (d_main == main_hi) ? main_lo : d_main + (uint32_t)stride;
               }
             }
+#ifdef TCT_PROFILE
+            const long long cm1 = clock64();
+            w2 += cm1 - cm0;
+#endif
             if (PAIR) umma_commit_pair_warp(bar_ae + 8u * sa);
             else umma_commit_warp(bar_ae + 8u * sa);
-            if (++sa == nas) { sa = 0; pa ^= 1u; }
+#ifdef TCT_PROFILE
+            w3 += clock64() - cm1;
+#endif
+            if (++sa == nas) sa = 0;
+            if (++fa == abars) { fa = 0; pa ^= 1u; }
           }
         }
+        if (pass_token) {                  // dual issue: this block's MMAs are in the pipe, the other warp may issue the next block
+          tc_fence_before();
+          mbar_arrive_elect(bar_tk + 8u * (uint32_t)(me ^ 1));
+        }
         if (PAIR) umma_commit_pair_warp(bar_be + 8u * sb);
-        else umma_commit_warp(bar_be + 8u * sb);
+        else TCT_TIMED(w3, umma_commit_warp(bar_be + 8u * sb));
         if (++sb == nsb) { sb = 0; pb ^= 1u; }
       };
+      // dual issue: the ring positions move over a k-block the other warp issues
+      auto skip = [&](int nks_here) {
+        for (int h = 0; h < (nks_here > 2 ? 2 : 1); ++h) {
+          if (++sa == nas) sa = 0;
+          if (++fa == abars) { fa = 0; pa ^= 1u; }
+        }
+        for (int j = 0; j < nks_here; ++j) d_main = (d_main == main_hi) ? main_lo : d_main + (uint32_t)stride;
+        if (++sb == nsb) { sb = 0; pb ^= 1u; }
+      };
+      // dual issue: everything this block needs is waited for BEFORE the token is taken, so that its twelve MMAs are issued
+      // back to back while this warp holds the right to issue
+      auto take = [&](int nks_here, bool need_token) {
+        if (!mma_only) {
+          TCT_TIMED(w0, mbar_wait(bar_bf + 8u * sb, pb));
+          TCT_TIMED(w1, mbar_wait(bar_af + 8u * fa, pa));
+          if (nks_here > 2) {
+            const int fan = (fa + 1 == abars) ? 0 : fa + 1;
+            TCT_TIMED(w1, mbar_wait(bar_af + 8u * fan, (fa + 1 == abars) ? (pa ^ 1u) : pa));
+          }
+        }
+        if (need_token) {
+          TCT_TIMED(w4, mbar_wait(bar_tk + 8u * (uint32_t)me, tok_par));
+          tok_par ^= 1u;
+        }
+      };
       const int nkb_full = nks >> 2;       // k-blocks whose four k-steps all carry data
+#ifdef TCT_PROFILE
+      if (warp == MMAW) TCT_PUT(2, clock64());
+#endif
       int kb = 0;
-      if (nkb_full > 0) { block(std::true_type{}, 4, 0); kb = 1; }
-      for (; kb < nkb_full; ++kb) block(std::false_type{}, 4, kb * 4);
-      if (kb < nkb) {
-        if (kb == 0) block(std::true_type{}, nks - kb * 4, 0);
-        else block(std::false_type{}, nks - kb * 4, kb * 4);
+      if (dual_issue) {
+        waited = true;
+        for (; kb < nkb; ++kb) {
+          const int nks_here = (nks - kb * 4 < 4) ? (nks - kb * 4) : 4;
+          if ((kb & 1) != me) { skip(nks_here); continue; }
+          take(nks_here, kb > 0);
+          pass_token = kb + 1 < nkb;
+          if (kb == 0) block(std::true_type{}, nks_here, 0);
+          else if (nks_here == 4) block(std::false_type{}, 4, kb * 4);
+          else block(std::false_type{}, nks_here, kb * 4);
+        }
+      } else {
+        if (nkb_full > 0) { block(std::true_type{}, 4, 0); kb = 1; }
+        for (; kb < nkb_full; ++kb) block(std::false_type{}, 4, kb * 4);
+        if (kb < nkb) {
+          if (kb == 0) block(std::true_type{}, nks - kb * 4, 0);
+          else block(std::false_type{}, nks - kb * 4, kb * 4);
+        }
       }
       if (PAIR) umma_commit_pair_warp(smem_u32(&bar_done));
-      else umma_commit_warp(smem_u32(&bar_done));
+      else umma_commit_warp(smem_u32(&bar_done));     // (dual issue: one arrival per issuing warp, each for its own MMAs)
+#ifdef TCT_PROFILE
+      if (warp == MMAW) { TCT_PUT(3, clock64()); TCT_PUT(6, w0); TCT_PUT(7, w1); TCT_PUT(16, w2); TCT_PUT(17, w3); TCT_PUT(18, w4); }
+#endif
     }
     __syncwarp();
   } else {
@@ -414,13 +564,20 @@ tc_tma_gemm_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapA, 
       const uint32_t bar_rf = smem_u32(&bar_raw_full[0]), bar_re = smem_u32(&bar_raw_empty[0]);
       const uint32_t bar_af = smem_u32(&bar_a_full[0]), bar_ae = smem_u32(&bar_a_empty[0]);
       RingPos rr = {0, 0};
+      const bool abl_a = (p.tune & 268435456) != 0;   // bring-up ablation: barrier protocol only (no LDS / split / tcgen05.st)
       int a_slot = ch;               // A-stage use n = 2 kb + ch -> slot n % nas, round n / nas (nas >= 2)
+      int a_bar = ch;                // ... and "full" barrier n % abars
       uint32_t a_round = 0;
-      for (int kb = 0; kb < nkb_feed; ++kb) {
-        mbar_wait(bar_rf + 8u * rr.slot, rr.round & 1u);
+      uint32_t hi[16], lo[16];
+      // raw tile of the next k-block -> this thread's hi / lo registers; the raw slot goes back to the TMA thread (8 arrivals)
+      auto load_split = [&]() {
+        TCT_TIMED(w0, mbar_wait(bar_rf + 8u * rr.slot, rr.round & 1u));
         const char* raw = smem_raw + (size_t)rr.slot * TCT_RAW_BYTES;
         float x[16];
-        if (A_KMAJOR) {
+        if (abl_a) {
+#pragma unroll
+          for (int k = 0; k < 16; ++k) x[k] = 0.f;
+        } else if (A_KMAJOR) {
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             const float4 v = *reinterpret_cast<const float4*>(raw + row * 128 + (((ch * 4 + c) ^ (row & 7)) << 4));
@@ -430,57 +587,104 @@ tc_tma_gemm_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapA, 
 #pragma unroll
           for (int k = 0; k < 16; ++k) x[k] = *reinterpret_cast<const float*>(raw + (ch * 16 + k) * 512 + row * 4);
         }
-        uint32_t hi[16], lo[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const float hv = tf32_hi(x[j]);
           hi[j] = __float_as_uint(hv);
           lo[j] = __float_as_uint(x[j] - hv);
         }
-        // this warp's values of the raw tile have been consumed: the slot goes back to the TMA thread (8 arrivals)
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_re + 8u * rr.slot);
         rr.next(TCT_NRAW);
-        if (kb * 4 + ch * 2 < nks) {                 // (uniform) this 16-k half carries data
+      };
+      // tune bit 262144: the loads and the split of the NEXT k-block run between the TMEM stores of this one and their
+      // tcgen05.wait::st (the converter is a serial chain per k-block; measured: profiles/tma_agents_r2.log)
+      const bool pipe_a = (p.tune & 262144) != 0;
+      if (pipe_a && nkb_feed > 0) load_split();
+      for (int kb = 0; kb < nkb_feed; ++kb) {
+        if (!pipe_a) load_split();
+        const bool has = kb * 4 + ch * 2 < nks;      // (uniform) this 16-k half carries data
+        const int bar_now = a_bar;
+        if (has) {
           if (a_round > 0) {
-            mbar_wait(bar_ae + 8u * a_slot, (a_round - 1) & 1u);   // the MMAs that read this stage are done
+            TCT_TIMED(w1, mbar_wait(bar_ae + 8u * a_slot, (a_round - 1) & 1u));   // the MMAs that read this stage are done
             tc_fence_after();
           }
           const uint32_t ta = t_lane + (uint32_t)(a_slot * 32);
-          tmem_st16(ta, hi);
-          tmem_st16(ta + 16u, lo);
-          tmem_st_wait();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_af + 8u * a_slot);
+          if (!abl_a) {
+            tmem_st16(ta, hi);
+            tmem_st16(ta + 16u, lo);
+          }
           a_slot += 2;
           while (a_slot >= nas) { a_slot -= nas; ++a_round; }
+          a_bar += 2;
+          while (a_bar >= abars) a_bar -= abars;
+        }
+        if (pipe_a && kb + 1 < nkb_feed) load_split();
+        if (has) {
+          if (!abl_a) tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_af + 8u * bar_now);
         }
       }
+#ifdef TCT_PROFILE
+      if (warp == CW0) { TCT_PUT(10, w0); TCT_PUT(11, w1); TCT_PUT(13, clock64() - loop0); }
+#endif
     } else if (BT) {
       // ===== B warps: the raw tile TMA wrote (SWIZZLE_128B) is split in place: hi over the raw bytes, lo into the twin =====
       const int f4_used = (((PAIR ? hp : n_valid) + 7) & ~7) * 8;   // whole 8-row swizzle atoms that hold stored rows
       constexpr int IT = (TC_BM * 8 + LT - 1) / LT;   // float4 items per thread (bn <= 128 rows x 8)
       RingPos rb = {0, 0};
+      const bool trunc_b = (p.tune & 33554432) != 0, abl_b = (p.tune & 536870912) != 0;
       for (int kb = 0; kb < nkb_feed; ++kb) {
-        mbar_wait(smem_u32(&bar_b_raw[rb.slot]), rb.round & 1u);
+        TCT_TIMED(w0, mbar_wait(smem_u32(&bar_b_raw[rb.slot]), rb.round & 1u));
         char* b_hi = smem_b + (size_t)rb.slot * bstage_bytes;
         char* b_lo = b_hi + b_bytes;
         float4 v[IT];
+        if (abl_b) {                       // bring-up ablation: barrier protocol only
+          mbar_arrive(smem_u32(&bar_b_full[rb.slot]));
+          rb.next(nsb);
+          continue;
+        }
 #pragma unroll
         for (int i = 0; i < IT; ++i) {
           const int f = tid + i * LT;
           if (f < f4_used) v[i] = *reinterpret_cast<const float4*>(b_hi + f * 16);
         }
+        if (trunc_b) {
+          // tune bit 33554432: the raw fp32 tile stays where TMA put it and serves as hi -- the tensor core reads the upper 19
+          // bits of a tf32 operand, i.e. hi = x truncated -- and only lo = tf32(x - trunc(x)) is written (exact difference,
+          // |lo| < 2^-10 |x|, rounded to the 11 bits the tensor core keeps so that no one-sided error is left). The weight
+          // operand keeps its ROUNDED split, so the dropped lo_w * lo_x term (< 2^-21 relative) has no preferred sign.
 #pragma unroll
-        for (int i = 0; i < IT; ++i) {
-          const int f = tid + i * LT;
-          if (f < f4_used) tc_split_store(b_hi, b_lo, (uint32_t)(f * 16), v[i]);
+          for (int i = 0; i < IT; ++i) {
+            const int f = tid + i * LT;
+            if (f < f4_used) {
+              float4 l;
+              l.x = tf32_hi(v[i].x - __uint_as_float(__float_as_uint(v[i].x) & 0xFFFFE000u));
+              l.y = tf32_hi(v[i].y - __uint_as_float(__float_as_uint(v[i].y) & 0xFFFFE000u));
+              l.z = tf32_hi(v[i].z - __uint_as_float(__float_as_uint(v[i].z) & 0xFFFFE000u));
+              l.w = tf32_hi(v[i].w - __uint_as_float(__float_as_uint(v[i].w) & 0xFFFFE000u));
+              *reinterpret_cast<float4*>(b_lo + f * 16) = l;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < IT; ++i) {
+            const int f = tid + i * LT;
+            if (f < f4_used) tc_split_store(b_hi, b_lo, (uint32_t)(f * 16), v[i]);
+          }
         }
+        // every thread orders its own generic-proxy stores before the async proxy and arrives (one arrival per warp after a
+        // __syncwarp was measured equal, profiles/tma_feed_abl_r2.log: the 256 arrivals are not what the loop costs)
         fence_proxy_async_smem();
         mbar_arrive(smem_u32(&bar_b_full[rb.slot]));
         rb.next(nsb);
       }
+#ifdef TCT_PROFILE
+      if (warp == 0) { TCT_PUT(12, w0); TCT_PUT(14, clock64() - loop0); }
+#endif
     } else {
       // ===== loader warps: B, global -> registers (TCT_DEPTH k-blocks in flight) -> split -> shared =====
       const Rows RB = resolve(p.B, g);
@@ -530,6 +734,9 @@ tc_tma_gemm_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapA, 
     constexpr int PARTS = (LWB + 8) / 4;
     mbar_wait(smem_u32(&bar_done), 0);
     tc_fence_after();
+#ifdef TCT_PROFILE
+    if (tid == 0) TCT_PUT(4, clock64());
+#endif
     const int crow = p.cidx ? p.cidx[g] : g;
     float* C = p.cbase + (long long)crow * p.c_gstride + p.c_off;
     const int n_used = nks < n_main ? nks : n_main;
@@ -612,6 +819,9 @@ tc_tma_gemm_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmapA, 
     }
   }
 
+#ifdef TCT_PROFILE
+  if (tid == 0) TCT_PUT(5, clock64());
+#endif
   tc_fence_before();
   if (PAIR) {
     cluster_sync_all();          // neither CTA leaves (or frees TMEM) while the other may still be read or signalled
@@ -665,10 +875,11 @@ static inline bool tct_plan(int N, int K, int rows0, int* bn_out, int* per_out, 
     const int per = (span + parts - 1) / parts;
     if (rows0 < N && span % per) continue;
     const int bn = (per + 15) / 16 * 16;
-    if (TC_TMEM_COLS - (1 + need) * bn >= 64) {
+    if (TC_TMEM_COLS - (1 + need) * bn >= 64 || ((tc_tune() & 1073741824) && TC_TMEM_COLS - 3 * bn >= 64)) {
       // as many hi*hi regions as still leave two A stages (up to 3, the rotation of the shared-memory-operand kernels: fewer
       // truncating accumulations per region than the cap asks for); tune bit 2097152: only the regions the cap needs
       int n_main = need;
+      if ((tc_tune() & 1073741824) && n_main > 2) n_main = 2;   // timing experiment only: more than TC_MAX_ACCUM accumulations per region
       if (!(tc_tune() & 2097152))
         while (n_main < 3 && TC_TMEM_COLS - (2 + n_main) * bn >= 64) ++n_main;
       const int nas = (TC_TMEM_COLS - (1 + n_main) * bn) / 32;
@@ -692,7 +903,7 @@ static inline void launch_tc_tma_inst(const TcParams& p, const CUtensorMap& mapA
   if (PAIR) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
-    cfg.blockDim = dim3((LWB + 10) * 32, 1, 1);
+    cfg.blockDim = dim3((LWB + 11) * 32, 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute at[1];
@@ -707,7 +918,7 @@ static inline void launch_tc_tma_inst(const TcParams& p, const CUtensorMap& mapA
     if (*err == cudaSuccess) *err = cudaGetLastError();
     return;
   }
-  tc_tma_gemm_kernel<A_KMAJOR, EPI, LWB, BT, PAIR><<<grid, (LWB + 10) * 32, smem, stream>>>(p, mapA, mapAt, mapB0, mapB1);
+  tc_tma_gemm_kernel<A_KMAJOR, EPI, LWB, BT, PAIR><<<grid, (LWB + 11) * 32, smem, stream>>>(p, mapA, mapAt, mapB0, mapB1);
   count_launch();
   *err = cudaGetLastError();
 }

@@ -27,12 +27,16 @@ def check(G, rows, din, dout):
     abi.check(abi.lib.cgl_linear_fwd(G, rows, din, dout, abi.ptr(x_d), rows * din, abi.ptr(prm_d), ld, None, 0, din * dout,
                                      abi.ACT_LRELU, 0.2, abi.ptr(y), rows * dout, st()))
     e_f = ((y.double().cpu() - y_ref).abs().max() / y_ref.abs().max()).item()
+    # signed error along the result's own sign (a one-sided split / accumulation error shows here, a symmetric one averages out)
+    b_f = (((y.double().cpu() - y_ref) * y_ref.sign()).mean() / y_ref.abs().mean()).item()
     dx = torch.empty(G, rows, din, device="cuda")
     abi.check(abi.lib.cgl_linear_bwd_data(G, rows, din, dout, abi.ptr(dy_d), rows * dout, abi.ptr(prm_d), ld, None, 0,
                                           abi.ptr(saved.cuda()), rows * din, abi.ACT_LRELU, 0.2, abi.ptr(dx), rows * din, st()))
     dx_ref = torch.bmm(dy.double(), W.double()) * torch.where(saved > 0, 1.0, 0.2)
     e_b = ((dx.double().cpu() - dx_ref).abs().max() / dx_ref.abs().max()).item()
-    print(f"check G={G} rows={rows} in={din} out={dout}: fwd err {e_f:.2e}  bwd err {e_b:.2e}", flush=True)
+    b_b = (((dx.double().cpu() - dx_ref) * dx_ref.sign()).mean() / dx_ref.abs().mean()).item()
+    print(f"check G={G} rows={rows} in={din} out={dout}: fwd err {e_f:.2e} (bias {b_f:+.1e})  bwd err {e_b:.2e} (bias {b_b:+.1e})",
+          flush=True)
     return max(e_f, e_b)
 
 

@@ -1,0 +1,12 @@
+# look-ahead barrier tests in the MMA warp (default) against none (tune bit 2)
+cd $GRAFT_REPO_ROOT
+BASE=$((1|8|32|64|256|512|1024|131072))
+for X in 2 0 2 0; do
+  echo "== extra bits $X"
+  CGL_TUNE=$((BASE|X)) timeout 120 python profiles/tma_probe.py fwd:1024:100:784 fwd:512:100:1024 fwd:784:200:512 bwd:1024:100:784 bwd:784:100:512 2>&1 | grep "bench"
+done
+CGL_TUNE=$BASE timeout 300 python profiles/pair_check.py 2>&1 | grep "check\|worst"
+export CGL_B200_LIB=$GRAFT_REPO_ROOT/cgl-gan_b200/lib/libcgl_prof.so
+for X in 2 0; do
+  CGL_TUNE=$((BASE|X)) timeout 120 python profiles/tma_agents.py fwd 1024 100 784 2>&1 | tail -7
+done

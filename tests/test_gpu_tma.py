@@ -112,3 +112,22 @@ def test_no_access_behind_an_operand_at_the_end_of_its_allocation(lib, kind, mod
         assert ((got.double() - ref).abs().max() / ref.abs().max()).item() < 2e-6
     finally:
         rt.cudaFree(p)
+
+
+# The opt-in variants of the TMA-fed kernel (CGL_TUNE is read once per process, so each runs in its own interpreter through
+# profiles/pair_check.py: every layer shape of a round against float64). 2: look-ahead barrier tests; 4: two issuing warps with a
+# token barrier (with 2 and, | 2097152, with 4 A stages); 262144: pipelined A converters; 33554432: truncated-hi batch operand.
+@pytest.mark.parametrize("extra", [2, 4, 4 | 2097152, 262144, 33554432])
+def test_opt_in_variants_match_float64(extra):
+    import os
+    import re
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    base = 1 | 8 | 32 | 64 | 256 | 512 | 1024 | 131072           # TC_TUNE_DEFAULT (csrc/tc_gemm.cuh)
+    env = dict(os.environ, CGL_TUNE=str(base | extra))
+    res = subprocess.run([sys.executable, os.path.join(root, "profiles", "pair_check.py")], capture_output=True, text=True,
+                         timeout=300, env=env)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    worst = float(re.search(r"worst error ([0-9.e+-]+)", res.stdout).group(1))
+    assert worst < 2e-6, res.stdout        # the default kernel: 1.0e-6 at K = 1024 (profiles/tma_shapes.py)
