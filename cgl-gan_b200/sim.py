@@ -118,6 +118,12 @@ class MDStyleSim:
         self.swap_rd = [Random(s + server_offset + 100) for s in range(self.S)]  # Server.rd, main.py:154-155
         self.profile = False              # bench: CUDA events around the client-step kernels
         self._events = []
+        # overlap_g: the generators' Xg pass runs on a second stream under the clients' D step (it is only needed by the G loss
+        # that follows the D step). Same kernels, same inputs, same order on every buffer: bit-identical results.
+        # (env CGL_OVERLAP_G=1 switches it on for measurements; measured: profiles/overlap_g_r2.log)
+        import os
+        self.overlap_g = os.environ.get("CGL_OVERLAP_G", "0") == "1"
+        self._side = None
 
     def client_step_ms(self):
         """Mean device time per round of the client-step calls (cgl_d_step + cgl_g_loss), from the CUDA
@@ -152,7 +158,20 @@ class MDStyleSim:
             z_g = torch.randn(S, B, 100, device=self.device)
         G = self.G
         Xd = G(z_d)          # no_grad pass of the reference: only its BatchNorm running statistics survive
-        Xg = G(z_g)          # the pass the generator is trained through
+        overlap = self.overlap_g and not self.profile and real.shape[0] == 1
+        if overlap:
+            # the Xg pass starts after the Xd pass (BatchNorm running statistics, shared workspace) on a second stream;
+            # the main stream goes on with the D step and waits for it before the G loss
+            main = torch.cuda.current_stream()
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=self.device)
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                Xg = G(z_g)
+            for t in (Xg,) + tuple(x for x in G._last if x is not None):
+                t.record_stream(main)      # allocated on the side stream, consumed (and freed) on the main stream
+        else:
+            Xg = G(z_g)          # the pass the generator is trained through
         shared = not self.multi_head
         if shared:           # one batch per server, seen by all of its clients (CGLGAN iid==0: Generator(ims, 1))
             Xd, Xg_flat = Xd.reshape(S, B, d), Xg.reshape(S, B, d)
@@ -167,8 +186,13 @@ class MDStyleSim:
             self.last_d_loss = self.bank.d_step(real[e], Xd, n_real=None if n_real is None else n_real[e],
                                                 fake_idx=idx)
         # the last D step and the G loss through the updated D: one ABI call (one launch for the 2DMG discriminator)
-        self.last_d_loss, loss, dxg = self.bank.client_step(real[E - 1], Xd, Xg_flat,
-                                                            n_real=None if n_real is None else n_real[E - 1], idx=idx)
+        if overlap:
+            self.last_d_loss = self.bank.d_step(real[0], Xd, n_real=None if n_real is None else n_real[0], fake_idx=idx)
+            torch.cuda.current_stream().wait_stream(self._side)
+            loss, dxg = self.bank.g_loss_raw(Xg_flat, xg_idx=idx)
+        else:
+            self.last_d_loss, loss, dxg = self.bank.client_step(real[E - 1], Xd, Xg_flat,
+                                                                n_real=None if n_real is None else n_real[E - 1], idx=idx)
         loss = loss.view(S, N)
         if self.profile:
             ev1 = torch.cuda.Event(enable_timing=True)
