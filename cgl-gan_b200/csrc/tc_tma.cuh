@@ -24,9 +24,16 @@
 // (16 k: [hi 16 | lo 16]); bn = 112 and K = 784 / 1024 leave exactly two.
 //
 // Warps: LWB B warps | 8 A converter warps (lane quarter = warp % 4, k-block half = warp / 4) | 1 MMA warp (converged,
-// the elected lane issues) | 1 TMA warp (one thread). Barriers: raw_full/raw_empty (TMA -> A converters), a_full/a_empty (A converters -> MMA, 16 k), b_raw (TMA -> B
-// warps), b_full/b_empty (B warps -> MMA -> TMA, 32 k), done. The epilogue (B + A converter warps) is the float4 one of
-// tc_gemm.cuh.
+// the elected lane issues) | 1 TMA warp (one thread) | 1 more MMA warp (idle unless CGL_TUNE bit 4 asks for two issuing warps).
+// Barriers: raw_full/raw_empty (TMA -> A converters), a_full (a ring of 2 x NAS barriers over the NAS stages) / a_empty
+// (A converters -> MMA, 16 k), b_raw (TMA -> B warps), b_full/b_empty (B warps -> MMA -> TMA, 32 k), tok (dual issue), done.
+// The epilogue (B + A converter warps) is the float4 one of tc_gemm.cuh.
+//
+// What paces it (profiles/tma_feed_abl_r2.log, tma_agents_r2.log): not the operand bytes and not the
+// shared-memory pipe -- dropping every TMA transfer or the hi store of the batch operand changes nothing -- but the
+// hand-shakes: ~1280 clk per k-block against 672 clk of MMAs, the A-stage round trip (commit -> converter -> tcgen05.st ->
+// arrive -> issue) where only two A stages fit, and each agent's serial chain per k-block right behind it. The bits
+// 2 / 4 / 262144 / 33554432 and the ablations 67108864 ... 1073741824 are the experiments of that analysis (TcParams::tune).
 #pragma once
 #include <cuda.h>
 #include <stdio.h>
