@@ -172,8 +172,34 @@ class ClockSampler:
 
     def __init__(self, index):
         self.samples, self.proc, self.index = [], None, index
+        self.nvml, self._stop = None, threading.Event()
+
+    def _poll_nvml(self, pynvml, handle):
+        # NVML in-process: a sample every 5 ms (nvidia-smi -lms 100 yields one to three samples in a 0.3 s timed region)
+        bits = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
+        while not self._stop.is_set():
+            try:
+                sm = pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM)
+                r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(handle)
+                self.nvml["sm"].append(float(sm))
+                for n, b in bits:
+                    if r & b:
+                        self.nvml["reasons"].add(n)
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.nvml = {"sm": [], "reasons": set(), "max": float(pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM))}
+            self.thread = threading.Thread(target=self._poll_nvml, args=(pynvml, handle), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -188,6 +214,12 @@ class ClockSampler:
             self.samples.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self._stop.set()
+            self.thread.join(timeout=2)
+            sm = sorted(self.nvml["sm"])
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.nvml["max"],
+                    "reasons": sorted(self.nvml["reasons"]), "samples": len(sm), "source": "nvml, 5 ms"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
