@@ -31,7 +31,7 @@
 //
 // What paces it (profiles/tma_feed_abl_r2.log, tma_agents_r2.log): not the operand bytes and not the
 // shared-memory pipe -- dropping every TMA transfer or the hi store of the batch operand changes nothing -- but the
-// hand-shakes: ~1280 clk per k-block against 672 clk of MMAs, the A-stage round trip (commit -> converter -> tcgen05.st ->
+// hand-shakes: ~1500 clk per k-block against ~700 clk of MMAs, the A-stage round trip (commit -> converter -> tcgen05.st ->
 // arrive -> issue) where only two A stages fit, and each agent's serial chain per k-block right behind it. The bits
 // 2 / 4 / 262144 / 33554432 and the ablations 67108864 ... 1073741824 are the experiments of that analysis (TcParams::tune).
 #pragma once
